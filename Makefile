@@ -1,0 +1,20 @@
+# Builds the C-ABI shared library of the hot path (sm_100a only) and the oracle has no native part.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v
+SRC := $(wildcard tcow_b200/csrc/*.cu)
+OBJ := $(patsubst tcow_b200/csrc/%.cu,build/%.o,$(SRC))
+LIB := tcow_b200/libtcow_b200.so
+
+all: $(LIB)
+
+build/%.o: tcow_b200/csrc/%.cu tcow_b200/csrc/ptx.cuh tcow_b200/csrc/tcow_internal.h include/tcow_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJ)
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -cudart static
+
+clean:
+	rm -rf build $(LIB)
+.PHONY: all clean

@@ -1,0 +1,107 @@
+/* tcow_b200 — C ABI of the B200 (sm_100a) Seeker-forward hot path.
+ *
+ * The reference (basilevh/tcow) is pure Python/PyTorch and has no FFI of its own; every entry point
+ * below replaces the torch.nn call(s) cited beside it (paths relative to the reference tree).  A
+ * maintainer binds them from Python with ctypes; `tcow_b200/_lib.py` is that
+ * binding.
+ *
+ * Conventions
+ *  - plain C types only; all pointers are DEVICE pointers owned by the caller (torch allocations);
+ *  - no allocation, no ownership transfer, no implicit synchronisation: work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *  - every function returns 0 on success or a negative TCOW_ERR_* code; `tcow_last_error()` returns a
+ *    thread-local message for the last failure on the calling thread;
+ *  - re-entrant: may be called concurrently from one thread per GPU (nn.DataParallel, train.py:223);
+ *    the device is the caller's current CUDA device;
+ *  - bf16 tensors are raw 16-bit bfloat16, fp32 tensors are IEEE float; "ld*" are row pitches in
+ *    ELEMENTS.
+ *
+ * Canonical activation layout ("token rows"): row r = (b*N + n)*T + t for clip b, patch n = ph*Wo+pw,
+ * frame t — the reference's token order x[b, 1 + n*T + t] (model/vision_tf.py:124,137; vit.py:170)
+ * without the cls token; the B cls rows are stored after the M = B*N*T patch rows (row M + b).
+ */
+#ifndef TCOW_B200_H_
+#define TCOW_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCOW_ERR_ARG (-1)   /* invalid argument (the reference raises AssertionError / ValueError) */
+#define TCOW_ERR_CUDA (-2)  /* CUDA runtime / driver failure, including launch errors */
+#define TCOW_ERR_ARCH (-3)  /* device is not compute capability 10.x — there is no fallback path */
+
+/* GEMM epilogues */
+#define TCOW_EPI_BF16 0      /* C(bf16)  = A W^T + bias                       (qkv: vit.py:81)          */
+#define TCOW_EPI_BF16_GELU 1 /* C(bf16)  = gelu_erf(A W^T + bias)             (Mlp.fc1+act: vit.py:55-56) */
+#define TCOW_EPI_F32_STORE 2 /* C(fp32)  = A W^T + bias                       (head: mask_tracker.py:113) */
+#define TCOW_EPI_F32_ADD 3   /* C(fp32) += A W^T + bias   (proj/temporal_fc/fc2 + residual: vit.py:176,215-216) */
+
+/* Library / device checks. */
+int tcow_abi_version(void);
+const char* tcow_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), else TCOW_ERR_ARCH. */
+int tcow_check_device(void);
+
+/* C[M,N] = epilogue(A[M,K] (bf16) x W[N,K]^T (bf16, nn.Linear layout) + bias[N] (fp32 or NULL)).
+ * tcgen05/TMEM tensor-core GEMM fed by TMA.  N and K multiples of 64; M arbitrary.
+ * Replaces nn.Linear at vit.py:50-52,73-74,146, mask_tracker.py:83-86 and the Conv2d at vit.py:233. */
+int tcow_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+                   int64_t ldc, int M, int N, int K, int epilogue, void* stream);
+
+/* y[rows,D] (bf16) = LayerNorm(x[rows,D] (fp32); gamma, beta, eps) with fp32 statistics
+ * (nn.LayerNorm(eps=1e-6): vit.py:135,142,150,428).  gamma == NULL: plain fp32 -> bf16 cast. */
+int tcow_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,
+                        float eps, void* stream);
+
+/* Temporal attention (Attention.forward with the BVH causal mask, vit.py:78-123, called at :172):
+ * for each of `num_seq` = B*N sequences of T consecutive token rows and each head,
+ *   out = softmax(q k^T * hd^-0.5 + mask) v,   mask: key j allowed for query i iff j <= i + causal_diag
+ * (causal_diag < 0 disables the mask; tril(0) -> 0, tril(d) -> d).  qkv is [rows, 3*heads*64] bf16 with
+ * column order [q | k | v], head-major (vit.py:81-82); out is [rows, heads*64] bf16.  T <= 64, hd = 64. */
+int tcow_attn_temporal(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int num_seq, int T,
+                       int heads, int causal_diag, void* stream);
+
+/* Spatial attention (vit.py:186 on the tokens assembled at :179-185): for each clip b, frame t, head:
+ * full softmax attention over [cls(b) ; patches n=0..N-1 of frame t] (use_cls=1) or the patches only
+ * (use_cls=0, causal_attention >= 2 or -1, vit.py:202-208).  Patch rows are read/written in place in the
+ * canonical layout (row (b*N+n)*T+t — no transposes); the cls q/k/v come from row cls_row0 + b of qkv.
+ * The cls query's output for every (b,t) goes to out_cls [B,T,heads*64] fp32. */
+int tcow_attn_spatial(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N,
+                      int T, int heads, int use_cls, int64_t cls_row0, void* stream);
+
+/* cls residual input (vit.py:191-198): out[cls_row0+b, :] (bf16) = out_cls[b,0,:] (mode 1, causal_attention==1)
+ * or mean_t out_cls[b,t,:] (mode 0, causal_attention==0). */
+int tcow_cls_merge(const float* out_cls, void* out, int64_t ld_out, int B, int T, int D, int64_t cls_row0,
+                   int mode, void* stream);
+
+/* Patch gather: builds the im2col matrix of the patch-embedding conv with the query mask concatenated as
+ * the 4th channel (mask_tracker.py:107-108, vit.py:235-238) in one pass:
+ *   P[(b*N+n)*T+t, c*256 + r*16 + w] (bf16) = x4[b,c,t,ph*16+r,pw*16+w],  x4 = cat(frames(3ch), query(1ch))
+ * frames [B,3,T,Hf,Wf] fp32, query [B,1,T,Hf,Wf] fp32.  normalize != 0 applies (x-0.45)/0.225 to the RGB
+ * channels only (vision_tf.py:81-89). */
+int tcow_patch_gather(const float* frames, const float* query, void* P, int B, int T, int Hf, int Wf,
+                      int patch, int normalize, void* stream);
+
+/* Residual-stream initialisation (vision_tf.py:99-138): X[(b*N+n)*T+t,:] = conv_bias + pos_embed[1+n] +
+ * time_embed[t];  X[M+b,:] = cls_token + pos_embed[0].  The patch GEMM then accumulates into X. */
+int tcow_embed_init(float* X, const float* conv_bias, const float* pos_embed, const float* time_embed,
+                    const float* cls_token, int B, int N, int T, int D, void* stream);
+
+/* Mask head tail (mask_tracker.py:114-132): `low` [M, ld_low] fp32 holds, per token, the avg-pooled
+ * C x pp x pp patch (column c*pp*pp + i*pp + j, pp = patch/stride; the pool is folded into the head
+ * weights); writes logits [B,C,T,Hf,Wf] fp32 = upsample x stride of the assembled (Ho*pp) x (Wo*pp) map.
+ * mode 0: bilinear, align_corners=True; mode 1: nearest. */
+int tcow_mask_upsample(const float* low, int64_t ld_low, float* out, int B, int T, int Ho, int Wo, int C,
+                       int pp, int stride, int mode, void* stream);
+
+/* Flags (mask_tracker.py:135-137): flags[b,t,f] = mean_n low[(b*N+n)*T+t, col0+f]. */
+int tcow_flag_mean(const float* low, int64_t ld_low, float* flags, int B, int N, int T, int F, int col0,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCOW_B200_H_ */

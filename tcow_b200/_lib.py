@@ -1,0 +1,66 @@
+"""ctypes binding of the C ABI in include/tcow_b200.h (libtcow_b200.so, built by `make` /
+``__graft_entry__.build()``).  There is no fallback: a missing library or a non-sm_100 device raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtcow_b200.so')
+
+TCOW_ERR_ARG, TCOW_ERR_CUDA, TCOW_ERR_ARCH = -1, -2, -3
+EPI_BF16, EPI_BF16_GELU, EPI_F32_STORE, EPI_F32_ADD = 0, 1, 2, 3
+
+# name -> argtypes (restype is int unless noted); mirrors include/tcow_b200.h one to one.
+SIGNATURES = {
+    'tcow_abi_version': [],
+    'tcow_last_error': [],
+    'tcow_check_device': [],
+    'tcow_gemm_bf16': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                       c_int, c_void_p],
+    'tcow_layernorm_bf16': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
+    'tcow_attn_temporal': [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p],
+    'tcow_attn_spatial': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                          c_int64, c_void_p],
+    'tcow_cls_merge': [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_int, c_void_p],
+    'tcow_patch_gather': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'tcow_embed_init': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'tcow_mask_upsample': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_void_p],
+    'tcow_flag_mean': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+}
+
+_lib = None
+
+
+class TcowError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TcowError(f'{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()); '
+                            'tcow_b200 has no fallback path')
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = c_char_p if name == 'tcow_last_error' else c_int
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an entry point; map error codes onto the exception types the reference raises."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.tcow_last_error().decode(errors='replace')
+        if rc == TCOW_ERR_ARG:
+            raise ValueError(f'{name}: {msg}')
+        raise TcowError(f'{name} failed ({rc}): {msg}')
+    return rc

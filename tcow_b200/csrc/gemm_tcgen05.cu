@@ -1,0 +1,317 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias[N]).
+//
+// Replaces every nn.Linear on the Seeker hot path of the reference
+// (third_party/TimeSformer/timesformer/models/vit.py:50-52 Mlp.fc1/fc2, :73-74 Attention.qkv/proj,
+// :146 temporal_fc; model/mask_tracker.py:83-86 head linears; vit.py:233 patch-embed conv as an
+// im2col GEMM).  A and W are both K-major (row-major activations, nn.Linear weight layout as is).
+//
+//   warp 0 (1 lane) : TMA producer   - cp.async.bulk.tensor 2-D loads, SWIZZLE_128B, 128x64 A + BNx64 W / stage
+//   warp 1 (1 lane) : MMA issuer     - tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16; fp32 accum in TMEM
+//   warp 2          : TMEM allocator - 2 accumulator stages x BN columns
+//   warps 4-7       : epilogue       - tcgen05.ld 32x32b -> +bias (-> exact-erf GELU) -> swizzled smem
+//                                      -> TMA store (bf16 / fp32) or TMA reduce-add into the fp32 residual stream
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), persistent tile loop.
+#include "ptx.cuh"
+#include "tcow_internal.h"
+
+namespace tcow {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+
+template <int BN, int STAGES, int EPI>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = BM * 128;  // staging chunk: 128 rows x 128 bytes
+  static constexpr int NUM_OUT = 2;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + NUM_OUT * OUT_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr bool OUT_F32 = (EPI == TCOW_EPI_F32_STORE || EPI == TCOW_EPI_F32_ADD);
+  static constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;
+  static constexpr int NCHUNK = BN / CHUNK_COLS;
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
+  static_assert(SMEM <= 232448, "exceeds 227 KB of shared memory");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+  using Cfg = GemmCfg<BN, STAGES, EPI>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t s_out = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bars = s_out + Cfg::NUM_OUT * Cfg::OUT_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+          const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, full_bar(s));
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * BK, n_blk * BN, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int acc = t & 1;
+        const uint32_t aph = (t >> 1) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in addr>>4 units
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------- epilogue (4 warps, one accumulator row per thread)
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;
+    const bool issuer = (threadIdx.x == 128);
+    uint32_t t = 0, cc = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int acc = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      mbar_wait(tfull_bar(acc), aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < Cfg::NCHUNK; ++c, ++cc) {
+        const uint32_t buf = s_out + (cc & 1) * Cfg::OUT_BYTES;
+        if (issuer) tma_wait_group_read<1>();  // the store issued two chunks ago has finished reading `buf`
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int col0 = n_blk * BN + c * Cfg::CHUNK_COLS;
+        const uint32_t srow = buf + row * 128;
+        const uint32_t sw = (row & 7);
+        if constexpr (Cfg::OUT_F32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (c == Cfg::NCHUNK - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + j) : make_float4(0, 0, 0, 0);
+            float4 o;
+            o.x = __uint_as_float(v[4 * j + 0]) + b.x;
+            o.y = __uint_as_float(v[4 * j + 1]) + b.y;
+            o.z = __uint_as_float(v[4 * j + 2]) + b.z;
+            o.w = __uint_as_float(v[4 * j + 3]) + b.w;
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((j ^ sw) << 4)), "f"(o.x), "f"(o.y),
+                         "f"(o.z), "f"(o.w)
+                         : "memory");
+          }
+        } else {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(t_row + c * 64, v0);
+          tmem_ld_32x32(t_row + c * 64 + 32, v1);
+          tmem_ld_wait();
+          if (c == Cfg::NCHUNK - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t* v = (j < 4) ? (v0 + 8 * j) : (v1 + 8 * (j - 4));
+            float4 b0 = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + 2 * j) : make_float4(0, 0, 0, 0);
+            float4 b1 =
+                bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + 2 * j + 1) : make_float4(0, 0, 0, 0);
+            float f[8];
+            f[0] = __uint_as_float(v[0]) + b0.x;
+            f[1] = __uint_as_float(v[1]) + b0.y;
+            f[2] = __uint_as_float(v[2]) + b0.z;
+            f[3] = __uint_as_float(v[3]) + b0.w;
+            f[4] = __uint_as_float(v[4]) + b1.x;
+            f[5] = __uint_as_float(v[5]) + b1.y;
+            f[6] = __uint_as_float(v[6]) + b1.z;
+            f[7] = __uint_as_float(v[7]) + b1.w;
+            if constexpr (EPI == TCOW_EPI_BF16_GELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((j ^ sw) << 4)),
+                         "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])),
+                         "r"(pack_bf16(f[6], f[7]))
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if constexpr (EPI == TCOW_EPI_F32_ADD)
+            tma_reduce_add_2d(&tmC, buf, col0, m_blk * BM);
+          else
+            tma_store_2d(&tmC, buf, col0, m_blk * BM);
+          tma_commit_group();
+        }
+      }
+    }
+    if (issuer) tma_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [rows, inner] with a row pitch; box = [box_rows, box_inner]; 128-byte swizzle.
+int make_tmap_2d(CUtensorMap* m, bool is_f32, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
+                 uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(TCOW_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const uint64_t es = is_f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((pitch_elems * es) & 15))
+    return set_error(TCOW_ERR_ARG, "tensor map: base and row pitch must be 16-byte aligned");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {pitch_elems * es};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(TCOW_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+template <int BN, int STAGES, int EPI>
+static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+                       int64_t ldc, int M, int N, int K, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, STAGES, EPI>;
+  alignas(64) CUtensorMap tmA, tmB, tmC;
+  int rc;
+  if ((rc = make_tmap_2d(&tmA, false, A, K, M, lda, BK, BM))) return rc;
+  if ((rc = make_tmap_2d(&tmB, false, W, K, N, ldw, BK, BN))) return rc;
+  if ((rc = make_tmap_2d(&tmC, Cfg::OUT_F32, C, N, M, ldc, Cfg::CHUNK_COLS, BM))) return rc;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES, EPI>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured[dev & 63] = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, 256, Cfg::SMEM, stream>>>(tmA, tmB, tmC, bias, M, N, K);
+  return check_launch("gemm_bf16_tn_kernel");
+}
+
+template <int EPI>
+static int dispatch_bn(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+                       int64_t ldc, int M, int N, int K, cudaStream_t stream) {
+  if (N % 256 == 0) return launch_gemm<256, 4, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  if (N % 128 == 0) return launch_gemm<128, 6, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  return launch_gemm<64, 8, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+}
+
+}  // namespace tcow
+
+extern "C" int tcow_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+                              int64_t ldc, int M, int N, int K, int epilogue, void* stream) {
+  using namespace tcow;
+  if (!A || !W || !C) return set_error(TCOW_ERR_ARG, "gemm: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(TCOW_ERR_ARG, "gemm: non-positive dimension");
+  if (N % 64 != 0 || K % 64 != 0)
+    return set_error(TCOW_ERR_ARG, "gemm: N (%d) and K (%d) must be multiples of 64", N, K);
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return set_error(TCOW_ERR_ARG, "gemm: bias must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (epilogue) {
+    case TCOW_EPI_BF16: return dispatch_bn<TCOW_EPI_BF16>(A, lda, W, ldw, bias, C, ldc, M, N, K, s);
+    case TCOW_EPI_BF16_GELU: return dispatch_bn<TCOW_EPI_BF16_GELU>(A, lda, W, ldw, bias, C, ldc, M, N, K, s);
+    case TCOW_EPI_F32_STORE: return dispatch_bn<TCOW_EPI_F32_STORE>(A, lda, W, ldw, bias, C, ldc, M, N, K, s);
+    case TCOW_EPI_F32_ADD: return dispatch_bn<TCOW_EPI_F32_ADD>(A, lda, W, ldw, bias, C, ldc, M, N, K, s);
+  }
+  return set_error(TCOW_ERR_ARG, "gemm: unknown epilogue %d", epilogue);
+}

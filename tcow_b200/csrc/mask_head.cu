@@ -1,0 +1,99 @@
+// Mask-decoding head tail: assemble the avg-pooled per-token patches into the low-resolution map and upsample
+// it (bilinear align_corners=True, or nearest) into fp32 logits; plus the per-frame flag mean.
+// Reference: model/mask_tracker.py:114-115 (pixel-shuffle rearrange), :118-132 (avg_pool2d + interpolate),
+// :135-137 (flag linear + spatial mean).  The avg-pool is folded into the head GEMM weights on the host
+// (tcow_b200/engine.py), so `low` already holds the pooled C x pp x pp values per token.
+// Write-bound: 4*C*Hf*Wf bytes per (clip, frame); one float4 store per thread, reads hit L2.
+#include "ptx.cuh"
+#include "tcow_internal.h"
+
+namespace tcow {
+
+__global__ void __launch_bounds__(256) mask_upsample_kernel(const float* __restrict__ low, int64_t ld_low,
+                                                            float* __restrict__ out, int B, int T, int Ho, int Wo,
+                                                            int C, int pp, int stride, int mode) {
+  const int Hl = Ho * pp, Wl = Wo * pp;
+  const int Hf = Hl * stride, Wf = Wl * stride;
+  const int N = Ho * Wo;
+  const int WV = Wf / 4;
+  const long long total = static_cast<long long>(B) * C * T * Hf * WV;
+  const long long gstride = static_cast<long long>(gridDim.x) * blockDim.x;
+  // PyTorch area_pixel_compute_scale(align_corners=True): (in-1)/(out-1), 0 when out == 1.
+  const float sy = (Hf > 1) ? static_cast<float>(Hl - 1) / static_cast<float>(Hf - 1) : 0.f;
+  const float sx = (Wf > 1) ? static_cast<float>(Wl - 1) / static_cast<float>(Wf - 1) : 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gstride) {
+    const int xv = static_cast<int>(i % WV);
+    long long r = i / WV;
+    const int y = static_cast<int>(r % Hf); r /= Hf;
+    const int t = static_cast<int>(r % T); r /= T;
+    const int c = static_cast<int>(r % C);
+    const int b = static_cast<int>(r / C);
+    auto fetch = [&](int ly, int lx) -> float {
+      const int n = (ly / pp) * Wo + (lx / pp);
+      const int col = (c * pp + (ly % pp)) * pp + (lx % pp);
+      return __ldg(low + ((static_cast<int64_t>(b) * N + n) * T + t) * ld_low + col);
+    };
+    float o[4];
+    if (mode == 1 || stride == 1) {  // nearest (scale_factor = stride): src = dst / stride
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = fetch(y / stride, (xv * 4 + e) / stride);
+    } else {
+      const float fy = sy * static_cast<float>(y);
+      const int y0 = static_cast<int>(fy);
+      const int y1 = y0 + ((y0 < Hl - 1) ? 1 : 0);
+      const float wy1 = fy - static_cast<float>(y0), wy0 = 1.f - wy1;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float fx = sx * static_cast<float>(xv * 4 + e);
+        const int x0 = static_cast<int>(fx);
+        const int x1 = x0 + ((x0 < Wl - 1) ? 1 : 0);
+        const float wx1 = fx - static_cast<float>(x0), wx0 = 1.f - wx1;
+        o[e] = wy0 * (wx0 * fetch(y0, x0) + wx1 * fetch(y0, x1)) + wy1 * (wx0 * fetch(y1, x0) + wx1 * fetch(y1, x1));
+      }
+    }
+    __stcs(reinterpret_cast<float4*>(out) + i, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// flags[b,t,f] = mean_n low[(b*N+n)*T+t, col0+f]; one warp per (b,t).
+__global__ void __launch_bounds__(128) flag_mean_kernel(const float* __restrict__ low, int64_t ld_low, float* __restrict__ flags,
+                                                        int B, int N, int T, int F, int col0) {
+  const int lane = threadIdx.x & 31;
+  const int bt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bt >= B * T) return;
+  const int b = bt / T, t = bt % T;
+  for (int f = 0; f < F; ++f) {
+    float s = 0.f;
+    for (int n = lane; n < N; n += 32) s += __ldg(low + ((static_cast<int64_t>(b) * N + n) * T + t) * ld_low + col0 + f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) flags[static_cast<int64_t>(bt) * F + f] = s / static_cast<float>(N);
+  }
+}
+
+}  // namespace tcow
+
+extern "C" int tcow_mask_upsample(const float* low, int64_t ld_low, float* out, int B, int T, int Ho, int Wo, int C,
+                                  int pp, int stride, int mode, void* stream) {
+  using namespace tcow;
+  if (!low || !out || B <= 0 || T <= 0 || Ho <= 0 || Wo <= 0 || C <= 0 || pp <= 0 || stride <= 0)
+    return set_error(TCOW_ERR_ARG, "mask_upsample: bad argument");
+  if ((Wo * pp * stride) % 4) return set_error(TCOW_ERR_ARG, "mask_upsample: frame width must be a multiple of 4");
+  if (mode != 0 && mode != 1) return set_error(TCOW_ERR_ARG, "mask_upsample: mode must be 0 (bilinear) or 1 (nearest)");
+  const long long total = static_cast<long long>(B) * C * T * (Ho * pp * stride) * (Wo * pp * stride / 4);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 32;
+  if (blocks > cap) blocks = cap;
+  mask_upsample_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(low, ld_low, out, B, T, Ho, Wo, C,
+                                                                                            pp, stride, mode);
+  return check_launch("mask_upsample_kernel");
+}
+
+extern "C" int tcow_flag_mean(const float* low, int64_t ld_low, float* flags, int B, int N, int T, int F, int col0,
+                              void* stream) {
+  using namespace tcow;
+  if (!low || !flags || B <= 0 || N <= 0 || T <= 0 || F <= 0) return set_error(TCOW_ERR_ARG, "flag_mean: bad argument");
+  const int bt = B * T;
+  flag_mean_kernel<<<(bt + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(low, ld_low, flags, B, N, T, F, col0);
+  return check_launch("flag_mean_kernel");
+}

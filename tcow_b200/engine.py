@@ -1,0 +1,247 @@
+"""The Seeker forward as a plan of sm_100a kernels (the product path; no eager / CPU fallback).
+
+Executes what the reference runs in model/mask_tracker.py:92-142 -> model/vision_tf.py:68-169 ->
+third_party/TimeSformer/timesformer/models/vit.py:155-217 (Block.forward, 12x), through the C ABI in
+include/tcow_b200.h.  Data layout in HBM:
+
+  X    fp32 [M+B, D]   residual stream, canonical token rows r=(b*N+n)*T+t, the B cls rows last
+  A    bf16 [M+B, D]   LayerNorm output (GEMM A operand)
+  QKV  bf16 [M+B, 3D]  qkv projections, columns [q|k|v] head-major
+  O    bf16 [M+B, D]   attention output (GEMM A operand)
+  H    bf16 [M+B, 4D]  GELU(fc1) (GEMM A operand); also holds the im2col patch matrix [M, 4*P*P]
+  LOW  fp32 [M, Npad]  pooled mask-head patch values + flag logits per token
+
+No tensor is ever transposed: the temporal kernels see T consecutive rows per (b,n), the spatial
+attention gathers rows with stride T, every GEMM is row-order agnostic.
+"""
+from __future__ import annotations
+
+import threading
+
+import torch
+
+from . import _lib, ops
+from .ops import EPI_BF16, EPI_BF16_GELU, EPI_F32_ADD, EPI_F32_STORE
+
+HEADS = 12
+
+
+class _Packed:
+    """Device-resident bf16 / folded copies of one module's parameters."""
+    pass
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class SeekerEngine:
+    def __init__(self, tracker, max_chunk=8, merge_temporal_proj=True):
+        self.max_chunk = max_chunk
+        # temporal_fc o temporal_attn.proj has no nonlinearity in between (vit.py:111 -> :174): at inference
+        # the two 768x768 linears are pre-multiplied in fp32 into one.
+        self.merge_temporal_proj = merge_temporal_proj
+        self._lock = threading.Lock()
+        self._packed = {}      # device index -> (stamp, _Packed)
+        self._workspace = {}   # (device index, Bc, shape key) -> dict of tensors
+        self.launches = 0      # kernels launched by the last forward (bench.py's gpu_launches)
+
+    # ------------------------------------------------------------------ weights
+    @staticmethod
+    def _stamp(mod):
+        return tuple((p.data_ptr(), p._version) for p in mod.parameters())
+
+    def _pack(self, mod, device):
+        bb = mod.tracker_backbone.timesformer.model
+        D = bb.embed_dim
+        P = mod.patch_size
+        bf = lambda t: _f32(t, device).to(torch.bfloat16).contiguous()
+        pk = _Packed()
+        pk.patch_w = bf(bb.patch_embed.proj.weight.reshape(D, -1))           # [D, 4*P*P], K = (c, r, w)
+        pk.patch_b = _f32(bb.patch_embed.proj.bias, device)
+        pk.pos = _f32(bb.pos_embed, device).reshape(-1, D)
+        pk.time = _f32(bb.time_embed, device).reshape(-1, D)
+        pk.cls = _f32(bb.cls_token, device).reshape(D)
+        pk.blocks = []
+        for blk in bb.blocks:
+            w = _Packed()
+            w.tn1 = (_f32(blk.temporal_norm1.weight, device), _f32(blk.temporal_norm1.bias, device))
+            w.n1 = (_f32(blk.norm1.weight, device), _f32(blk.norm1.bias, device))
+            w.n2 = (_f32(blk.norm2.weight, device), _f32(blk.norm2.bias, device))
+            w.t_qkv = (bf(blk.temporal_attn.qkv.weight), _f32(blk.temporal_attn.qkv.bias, device))
+            Wp, bp = _f32(blk.temporal_attn.proj.weight, device), _f32(blk.temporal_attn.proj.bias, device)
+            Wf, bfc = _f32(blk.temporal_fc.weight, device), _f32(blk.temporal_fc.bias, device)
+            if self.merge_temporal_proj:
+                # fc(proj(o)) = o (Wf Wp)^T + (Wf bp + bf); exact fp32 products (TF32 off), then one bf16 rounding
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                try:
+                    w.t_out = ((Wf @ Wp).to(torch.bfloat16).contiguous(), (Wf @ bp + bfc).contiguous())
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev
+                w.t_proj = w.t_fc = None
+            else:
+                w.t_out = None
+                w.t_proj = (Wp.to(torch.bfloat16).contiguous(), bp)
+                w.t_fc = (Wf.to(torch.bfloat16).contiguous(), bfc)
+            w.s_qkv = (bf(blk.attn.qkv.weight), _f32(blk.attn.qkv.bias, device))
+            w.s_proj = (bf(blk.attn.proj.weight), _f32(blk.attn.proj.bias, device))
+            w.fc1 = (bf(blk.mlp.fc1.weight), _f32(blk.mlp.fc1.bias, device))
+            w.fc2 = (bf(blk.mlp.fc2.weight), _f32(blk.mlp.fc2.bias, device))
+            pk.blocks.append(w)
+        pk.norm = (_f32(bb.norm.weight, device), _f32(bb.norm.bias, device))
+        # Head: fold avg_pool2d(stride) into tracker_post_linear (mask_tracker.py:113-122; pooling is linear and
+        # acts inside one patch because stride | P), append the flag rows, pad N to a multiple of 64.
+        C, s = mod.output_channels, max(int(mod.track_map_stride), 1)
+        if P % s != 0:
+            raise NotImplementedError(f'track_map_stride={s} must divide patch_size={P}')
+        pp = P // s
+        Wt, bt = _f32(mod.tracker_post_linear.weight, device), _f32(mod.tracker_post_linear.bias, device)
+        Wt = Wt.reshape(C, pp, s, pp, s, D).mean((2, 4)).reshape(C * pp * pp, D)
+        bt = bt.reshape(C, pp, s, pp, s).mean((2, 4)).reshape(-1)
+        rows, biases = [Wt], [bt]
+        F = mod.flag_channels
+        if F > 0:
+            rows.append(_f32(mod.flag_post_linear.weight, device))
+            biases.append(_f32(mod.flag_post_linear.bias, device))
+        n_used = C * pp * pp + max(F, 0)
+        n_pad = (n_used + 63) // 64 * 64
+        Wh = torch.zeros(n_pad, D, device=device, dtype=torch.float32)
+        bh = torch.zeros(n_pad, device=device, dtype=torch.float32)
+        Wh[:n_used] = torch.cat(rows, 0)
+        bh[:n_used] = torch.cat(biases, 0)
+        pk.head_w, pk.head_b = Wh.to(torch.bfloat16).contiguous(), bh
+        pk.pp, pk.stride, pk.flag_col0, pk.n_pad = pp, s, C * pp * pp, n_pad
+        return pk
+
+    def packed(self, mod, device):
+        stamp = (self._stamp(mod), self.merge_temporal_proj)
+        with self._lock:
+            hit = self._packed.get(device.index)
+            if hit is not None and hit[0] == stamp:
+                return hit[1]
+        with torch.no_grad():
+            pk = self._pack(mod, device)
+        with self._lock:
+            self._packed[device.index] = (stamp, pk)
+        return pk
+
+    def _ws(self, device, Bc, N, T, D, K_patch, n_pad):
+        key = (device.index, Bc, N, T, D, K_patch, n_pad)
+        with self._lock:
+            ws = self._workspace.get(key)
+        if ws is None:
+            M = Bc * N * T
+            R = M + Bc
+            e = lambda shape, dt: torch.empty(shape, device=device, dtype=dt)
+            ws = dict(X=e((R, D), torch.float32), A=e((R, D), torch.bfloat16), QKV=e((R, 3 * D), torch.bfloat16),
+                      O=e((R, D), torch.bfloat16), H=e((R * max(4 * D, K_patch),), torch.bfloat16),
+                      OCLS=e((Bc, T, D), torch.float32), LOW=e((M, n_pad), torch.float32))
+            with self._lock:
+                self._workspace[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, mod, input_frames, query_mask):
+        if not input_frames.is_cuda:
+            raise RuntimeError('tcow_b200 runs on a CUDA sm_100 device only; move the module and inputs to '
+                               'the GPU (there is no CPU fallback)')
+        if torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters()):
+            raise NotImplementedError('tcow_b200 round 1 implements the forward only; call under '
+                                      'torch.no_grad() (as pipeline.py set_phase("test") does)')
+        device = input_frames.device
+        bbm = mod.tracker_backbone
+        B, Cin, T, Hf, Wf = input_frames.shape
+        if Cin != 3:
+            raise RuntimeError(f'expected 3 RGB channels (+1 query channel = in_chans 4), got {Cin}')
+        if tuple(query_mask.shape) != (B, 1, T, Hf, Wf):
+            raise RuntimeError(f'query_mask shape {tuple(query_mask.shape)} does not match frames {tuple(input_frames.shape)}')
+        assert T == bbm.T                                   # vision_tf.py:96
+        assert Hf == bbm.Hf and Wf == bbm.Wf                # pos_embed is built for this grid (vision_tf.py:97)
+        P, D = mod.patch_size, bbm.output_feature_dim
+        Ho, Wo = Hf // P, Wf // P
+        N = Ho * Wo
+        causal = int(mod.causal_attention)
+        if causal in (0, 1):
+            use_cls = True
+        elif causal >= 2 or causal == -1:
+            use_cls = False
+        else:
+            raise ValueError(f'unsupported causal_attention={causal}')  # vit.py:179-208 has no branch either
+        causal_diag = -1 if causal <= 0 else (0 if causal <= 2 else causal - 2)   # vit.py:93-99
+        if mod.track_map_resize not in ('bilinear', 'nearest'):
+            # mask_tracker.py:124-130 silently skips the resize for other values; reject instead of guessing
+            raise ValueError(f'unsupported track_map_resize={mod.track_map_resize!r}')
+
+        with torch.cuda.device(device):
+            _lib.call('tcow_check_device')
+            pk = self.packed(mod, device)
+            frames = input_frames.to(torch.float32).contiguous()
+            query = query_mask.to(torch.float32).contiguous()
+            C, F = mod.output_channels, mod.flag_channels
+            out_mask = torch.empty((B, C, T, Hf, Wf), device=device, dtype=torch.float32)
+            out_flags = torch.empty((B, T, F), device=device, dtype=torch.float32) if F > 0 else None
+            self.launches = 0
+            for b0 in range(0, B, self.max_chunk):
+                b1 = min(B, b0 + self.max_chunk)
+                self._run_chunk(mod, pk, frames[b0:b1], query[b0:b1], out_mask[b0:b1],
+                                None if out_flags is None else out_flags[b0:b1],
+                                N, T, D, P, Ho, Wo, use_cls, causal, causal_diag)
+        return out_mask, out_flags
+
+    def _run_chunk(self, mod, pk, frames, query, out_mask, out_flags, N, T, D, P, Ho, Wo, use_cls, causal,
+                   causal_diag):
+        Bc = frames.shape[0]
+        M = Bc * N * T
+        R = M + Bc
+        Kp = 4 * P * P
+        ws = self._ws(frames.device, Bc, N, T, D, Kp, pk.n_pad)
+        X, A, QKV, O, OCLS, LOW = ws['X'], ws['A'], ws['QKV'], ws['O'], ws['OCLS'], ws['LOW']
+        H = ws['H'][:R * 4 * D].view(R, 4 * D)
+        PM = ws['H'][:M * Kp].view(M, Kp)
+        n = 0
+        # ---- patch embedding + embeddings (mask_tracker.py:107-108, vit.py:235-241, vision_tf.py:99-138)
+        ops.patch_gather(frames, query, PM, P, bool(mod.tracker_backbone.pretrained))
+        ops.embed_init(X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D)
+        ops.gemm(PM, pk.patch_w, None, X[:M], EPI_F32_ADD)
+        n += 3
+        Rs = R if use_cls else M
+        for w in pk.blocks:
+            # temporal attention + temporal_fc + residual (vit.py:169-176); cls rows untouched
+            ops.layernorm(X[:M], w.tn1[0], w.tn1[1], A[:M])
+            ops.gemm(A[:M], w.t_qkv[0], w.t_qkv[1], QKV[:M], EPI_BF16)
+            ops.attn_temporal(QKV, O, Bc * N, T, HEADS, causal_diag)
+            if w.t_out is not None:
+                ops.gemm(O[:M], w.t_out[0], w.t_out[1], X[:M], EPI_F32_ADD)
+                n += 4
+            else:
+                ops.gemm(O[:M], w.t_proj[0], w.t_proj[1], A[:M], EPI_BF16)
+                ops.gemm(A[:M], w.t_fc[0], w.t_fc[1], X[:M], EPI_F32_ADD)
+                n += 5
+            # spatial attention + residual (vit.py:179-215); cls is key/query 0 of every frame
+            ops.layernorm(X[:Rs], w.n1[0], w.n1[1], A[:Rs])
+            ops.gemm(A[:Rs], w.s_qkv[0], w.s_qkv[1], QKV[:Rs], EPI_BF16)
+            ops.attn_spatial(QKV, O, OCLS if use_cls else None, Bc, N, T, HEADS, use_cls, M)
+            n += 3
+            if use_cls:
+                ops.cls_merge(OCLS, O, Bc, T, D, M, 1 if causal == 1 else 0)
+                n += 1
+            ops.gemm(O[:Rs], w.s_proj[0], w.s_proj[1], X[:Rs], EPI_F32_ADD)
+            # MLP on every token incl. cls (vit.py:216)
+            ops.layernorm(X, w.n2[0], w.n2[1], A)
+            ops.gemm(A, w.fc1[0], w.fc1[1], H, EPI_BF16_GELU)
+            ops.gemm(H, w.fc2[0], w.fc2[1], X, EPI_F32_ADD)
+            n += 4
+        # ---- optional final norm (vision_tf.py:152-153) or plain cast, then head (mask_tracker.py:112-137)
+        if mod.norm_embeddings:
+            ops.layernorm(X[:M], pk.norm[0], pk.norm[1], A[:M])
+        else:
+            ops.layernorm(X[:M], None, None, A[:M])
+        ops.gemm(A[:M], pk.head_w, pk.head_b, LOW, EPI_F32_STORE)
+        mode = 1 if (mod.track_map_resize == 'nearest' or pk.stride == 1) else 0
+        ops.mask_upsample(LOW, out_mask, Bc, T, Ho, Wo, mod.output_channels, pk.pp, pk.stride, mode)
+        n += 3
+        if out_flags is not None:
+            ops.flag_mean(LOW, out_flags, Bc, N, T, mod.flag_channels, pk.flag_col0)
+            n += 1
+        self.launches += n

@@ -1,0 +1,84 @@
+"""Drop-in for model/mask_tracker.py: QueryMaskTracker with the reference's constructor, parameters and
+forward contract (model/mask_tracker.py:24-28, :92-142); the arithmetic runs on sm_100a CUDA kernels."""
+from __future__ import annotations
+
+import torch
+
+from . import vision_tf
+from .engine import SeekerEngine
+
+
+class QueryMaskTracker(torch.nn.Module):
+
+    def __init__(self, logger, num_total_frames=24, num_visible_frames=16, frame_height=224, frame_width=288,
+                 tracker_pretrained=False, attention_type='divided_space_time', patch_size=16,
+                 causal_attention=False, norm_embeddings=False, drop_path_rate=0.1, network_depth=12,
+                 track_map_stride=4, track_map_resize='bilinear', query_channels=1, output_channels=3,
+                 flag_channels=3):
+        super().__init__()
+        self.logger = logger
+        self.num_total_frames = num_total_frames
+        self.num_visible_frames = num_visible_frames
+        self.frame_height = frame_height
+        self.frame_width = frame_width
+        self.attention_type = attention_type
+        self.patch_size = patch_size
+        self.causal_attention = causal_attention
+        self.norm_embeddings = norm_embeddings
+        self.drop_path_rate = drop_path_rate
+        self.network_depth = network_depth
+        self.track_map_stride = track_map_stride
+        self.track_map_resize = track_map_resize
+        self.query_channels = query_channels
+        self.output_channels = output_channels
+        self.flag_channels = flag_channels
+        self.input_channels = 3 + self.query_channels
+
+        # mask_tracker.py:52-69 — same parsing of the pretrained flag / path.
+        self.pretrained_path = ''
+        if isinstance(tracker_pretrained, bool):
+            self.tracker_pretrained = tracker_pretrained
+        elif isinstance(tracker_pretrained, str):
+            if tracker_pretrained.lower() in ['1', 'y', 'yes', 't', 'true']:
+                self.tracker_pretrained = True
+            elif len(tracker_pretrained) <= 5:
+                self.tracker_pretrained = False
+            else:
+                self.tracker_pretrained = True
+                self.pretrained_path = tracker_pretrained
+        else:
+            raise ValueError(f'Invalid tracker_pretrained value: {tracker_pretrained}.')
+        self.logger.info(f'(QueryMaskTracker) tracker_pretrained: {self.tracker_pretrained} '
+                         f'pretrained_path: {self.pretrained_path}')
+        if self.query_channels != 1:
+            raise NotImplementedError('tcow_b200 supports query_channels=1 (train.py:202 hard-codes it)')
+
+        self.tracker_backbone = vision_tf.MyDenseTimeSformerBackbone(
+            self.logger, num_frames=self.num_total_frames, frame_height=self.frame_height,
+            frame_width=self.frame_width, patch_dim=self.patch_size, in_channels=self.input_channels,
+            pretrained=self.tracker_pretrained, pretrained_path=self.pretrained_path,
+            attention_type=self.attention_type, causal_attention=self.causal_attention,
+            norm_embeddings=self.norm_embeddings, drop_path_rate=self.drop_path_rate,
+            network_depth=self.network_depth)
+        self.use_feature_dim = self.tracker_backbone.output_feature_dim
+        self.tracker_post_linear = torch.nn.Linear(
+            self.use_feature_dim, self.output_channels * self.patch_size * self.patch_size)
+        if self.flag_channels > 0:
+            self.flag_post_linear = torch.nn.Linear(self.use_feature_dim, self.flag_channels)
+        assert self.frame_height % self.patch_size == 0
+        assert self.frame_width % self.patch_size == 0
+        self._engine = None  # built lazily on the parameters' device; not part of the state dict
+
+    def engine(self):
+        if self._engine is None:
+            self._engine = SeekerEngine(self)
+        return self._engine
+
+    def forward(self, input_frames, query_mask):
+        '''
+        :param input_frames (B, 3, T, Hf, Wf) tensor.
+        :param query_mask (B, 1, T, Hf, Wf) tensor.
+        :return (output_mask (B, C, T, Hf, Wf) fp32 logits, output_flags (B, T, F) fp32 or None).
+        '''
+        assert query_mask.shape[1] == 1                         # mask_tracker.py:105
+        return self.engine().forward(self, input_frames, query_mask)

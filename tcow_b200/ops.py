@@ -1,0 +1,97 @@
+"""Torch-tensor front end of the C ABI: pointer/shape plumbing only (PyTorch owns memory and streams)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BF16, EPI_BF16_GELU, EPI_F32_ADD, EPI_F32_STORE  # noqa: F401
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name}: tensor must live on a CUDA device (tcow_b200 has no CPU path)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if t.dim() >= 1 and t.stride(-1) != 1:
+        raise ValueError(f'{name}: innermost dimension must be contiguous')
+
+
+def gemm(a, w, bias, out, epilogue):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias); a, w bf16; out bf16 or fp32 by epilogue."""
+    _chk(a, torch.bfloat16, 'gemm.a'); _chk(w, torch.bfloat16, 'gemm.w')
+    _chk(out, torch.float32 if epilogue in (EPI_F32_STORE, EPI_F32_ADD) else torch.bfloat16, 'gemm.out')
+    if bias is not None:
+        _chk(bias, torch.float32, 'gemm.bias')
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or out.shape[0] != M or out.shape[1] != N:
+        raise ValueError(f'gemm: shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}')
+    _lib.call('tcow_gemm_bf16', a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _p(bias), out.data_ptr(),
+              out.stride(0), M, N, K, epilogue, _stream())
+    return out
+
+
+def layernorm(x, gamma, beta, out, eps=1e-6):
+    _chk(x, torch.float32, 'layernorm.x'); _chk(out, torch.bfloat16, 'layernorm.out')
+    rows, D = x.shape
+    if not (x.is_contiguous() and out.is_contiguous() and out.shape == x.shape):
+        raise ValueError('layernorm: x and out must be contiguous and of equal shape')
+    _lib.call('tcow_layernorm_bf16', x.data_ptr(), _p(gamma), _p(beta), out.data_ptr(), rows, D, float(eps), _stream())
+    return out
+
+
+def attn_temporal(qkv, out, num_seq, T, heads, causal_diag):
+    _chk(qkv, torch.bfloat16, 'attn_temporal.qkv'); _chk(out, torch.bfloat16, 'attn_temporal.out')
+    _lib.call('tcow_attn_temporal', qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), num_seq, T, heads,
+              causal_diag, _stream())
+    return out
+
+
+def attn_spatial(qkv, out, out_cls, B, N, T, heads, use_cls, cls_row0):
+    _chk(qkv, torch.bfloat16, 'attn_spatial.qkv'); _chk(out, torch.bfloat16, 'attn_spatial.out')
+    if out_cls is not None:
+        _chk(out_cls, torch.float32, 'attn_spatial.out_cls')
+    _lib.call('tcow_attn_spatial', qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), _p(out_cls), B, N, T,
+              heads, int(use_cls), cls_row0, _stream())
+    return out
+
+
+def cls_merge(out_cls, out, B, T, D, cls_row0, mode):
+    _lib.call('tcow_cls_merge', out_cls.data_ptr(), out.data_ptr(), out.stride(0), B, T, D, cls_row0, mode, _stream())
+
+
+def patch_gather(frames, query, out, patch, normalize):
+    _chk(frames, torch.float32, 'patch_gather.frames'); _chk(query, torch.float32, 'patch_gather.query')
+    _chk(out, torch.bfloat16, 'patch_gather.out')
+    B, C, T, Hf, Wf = frames.shape
+    if C != 3 or tuple(query.shape) != (B, 1, T, Hf, Wf) or not (frames.is_contiguous() and query.is_contiguous()):
+        raise ValueError('patch_gather: frames (B,3,T,H,W) and query (B,1,T,H,W) must be contiguous')
+    _lib.call('tcow_patch_gather', frames.data_ptr(), query.data_ptr(), out.data_ptr(), B, T, Hf, Wf, patch,
+              int(normalize), _stream())
+    return out
+
+
+def embed_init(X, conv_bias, pos_embed, time_embed, cls_token, B, N, T, D):
+    _lib.call('tcow_embed_init', X.data_ptr(), conv_bias.data_ptr(), pos_embed.data_ptr(), time_embed.data_ptr(),
+              cls_token.data_ptr(), B, N, T, D, _stream())
+    return X
+
+
+def mask_upsample(low, out, B, T, Ho, Wo, C, pp, stride, mode):
+    _chk(low, torch.float32, 'mask_upsample.low'); _chk(out, torch.float32, 'mask_upsample.out')
+    _lib.call('tcow_mask_upsample', low.data_ptr(), low.stride(0), out.data_ptr(), B, T, Ho, Wo, C, pp, stride, mode,
+              _stream())
+    return out
+
+
+def flag_mean(low, flags, B, N, T, F, col0):
+    _lib.call('tcow_flag_mean', low.data_ptr(), low.stride(0), flags.data_ptr(), B, N, T, F, col0, _stream())
+    return flags

@@ -1,0 +1,144 @@
+"""Host-side logic that needs no GPU: state-dict layout, constructor contract, C-ABI symbols, weight folding."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import tcow_b200
+from tcow_b200 import _lib, synth
+from tcow_b200.engine import SeekerEngine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KW = dict(num_total_frames=4, num_visible_frames=4, frame_height=32, frame_width=48, tracker_pretrained=False,
+          attention_type='divided_space_time', patch_size=16, causal_attention=1, norm_embeddings=False,
+          drop_path_rate=0.1, network_depth=12, track_map_stride=4, track_map_resize='bilinear',
+          query_channels=1, output_channels=3, flag_channels=3)
+
+
+@pytest.fixture(scope='module')
+def net(logger):
+    return tcow_b200.Seeker(logger, **KW)
+
+
+def test_state_dict_layout_matches_reference(net):
+    """251 tensors with the names/shapes of checkpoint['net_seeker'] (train.py:281)."""
+    want = synth.state_dict_shapes(num_frames=4, frame_height=32, frame_width=48)
+    got = net.state_dict()
+    assert len(got) == 251
+    assert list(got.keys()) == list(want.keys())
+    for k, shp in want.items():
+        assert tuple(got[k].shape) == tuple(shp), k
+        assert got[k].dtype == torch.float32
+    assert sum(p.numel() for p in net.parameters()) == sum(torch.Size(s).numel() for s in want.values())
+
+
+def test_param_count_north_star(logger):
+    shapes = synth.state_dict_shapes(num_frames=30, frame_height=240, frame_width=320)
+    assert sum(torch.Size(s).numel() for s in shapes.values()) == 122145027
+
+
+def test_reference_init_semantics(net):
+    """vit.py:264-306: time_embed and every temporal_fc are zero, biases zero, LN (1,0)."""
+    bb = net.seeker.tracker_backbone.timesformer.model
+    assert bb.time_embed.abs().max() == 0
+    for blk in bb.blocks:
+        assert blk.temporal_fc.weight.abs().max() == 0 and blk.temporal_fc.bias.abs().max() == 0
+        assert blk.attn.qkv.bias.abs().max() == 0
+        assert torch.all(blk.norm1.weight == 1) and torch.all(blk.norm1.bias == 0)
+        assert 0.018 < blk.mlp.fc1.weight.std() < 0.022 and blk.mlp.fc1.weight.abs().max() <= 2.0
+    assert net.seeker.tracker_post_linear.weight.abs().max() <= 768 ** -0.5 + 1e-6  # torch default Linear init
+
+
+def test_state_dict_roundtrip(net, logger):
+    sd = synth.make_state_dict(7, num_frames=4, frame_height=32, frame_width=48)
+    net2 = tcow_b200.Seeker(logger, **KW)
+    net2.load_state_dict(sd, strict=True)
+    for k, v in net2.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_constructor_contract(logger):
+    with pytest.raises(ValueError):
+        tcow_b200.Seeker(logger, **{**KW, 'tracker_pretrained': 3.5})       # mask_tracker.py:67
+    with pytest.raises(ValueError):
+        tcow_b200.Seeker(logger, **{**KW, 'network_depth': 13})             # vit.py:449
+    with pytest.raises(AssertionError):
+        tcow_b200.Seeker(logger, **{**KW, 'frame_height': 40})              # mask_tracker.py:89
+    with pytest.raises(AssertionError):
+        tcow_b200.Seeker(logger, **{**KW, 'attention_type': 'bogus'})       # vit.py:133
+    m = tcow_b200.Seeker(logger, **{**KW, 'tracker_pretrained': 'no'})      # short string -> False
+    assert m.seeker.tracker_pretrained is False
+    m = tcow_b200.Seeker(logger, **{**KW, 'flag_channels': 0})
+    assert not hasattr(m.seeker, 'flag_post_linear') and len(m.state_dict()) == 249
+
+
+def test_cpu_forward_fails_loudly(net):
+    rgb, q = synth.make_batch([0], num_frames=4, frame_height=32, frame_width=48)
+    with torch.no_grad(), pytest.raises(RuntimeError, match='CUDA'):
+        net(rgb, q)
+    with pytest.raises(AssertionError):
+        net(rgb, torch.cat([q, q], 1))                                      # mask_tracker.py:105
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports exactly what include/tcow_b200.h declares."""
+    hdr = open(os.path.join(ROOT, 'include', 'tcow_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(tcow_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} not exported'
+    assert _lib.load().tcow_abi_version() == 1
+
+
+def test_library_rejects_bad_arguments_without_gpu():
+    with pytest.raises(ValueError, match='multiples of 64'):
+        _lib.call('tcow_gemm_bf16', 16, 64, 16, 64, None, 16, 100, 128, 100, 64, 0, None)
+    with pytest.raises(ValueError):
+        _lib.call('tcow_attn_temporal', 16, 2304, 16, 768, 10, 65, 12, 0, None)
+    with pytest.raises(ValueError):
+        _lib.call('tcow_layernorm_bf16', 16, 16, 16, 16, 8, 100, 1e-6, None)
+
+
+def test_head_fold_equals_pool_then_linear(net):
+    """avg_pool2d folded into tracker_post_linear == reference order (mask_tracker.py:113-122)."""
+    torch.manual_seed(0)
+    mod = net.seeker
+    with torch.no_grad():
+        mod.tracker_post_linear.weight.normal_(0, 0.05)
+        mod.tracker_post_linear.bias.normal_(0, 0.05)
+        mod.flag_post_linear.weight.normal_(0, 0.05)
+    eng = SeekerEngine(mod)
+    pk = eng._pack(mod, torch.device('cpu'))
+    assert pk.pp == 4 and pk.stride == 4 and pk.flag_col0 == 48 and pk.n_pad == 64
+    feat = torch.randn(5, 768)
+    ref = F.linear(feat, mod.tracker_post_linear.weight, mod.tracker_post_linear.bias).reshape(5, 3, 16, 16)
+    ref = F.avg_pool2d(ref, 4, 4).reshape(5, 48)
+    Wh = pk.head_w.float()
+    got = feat.to(torch.bfloat16).float() @ Wh.t() + pk.head_b
+    assert (got[:, :48] - ref).abs().max() < 0.05
+    # exact check in fp32 (undo the bf16 rounding of the packed copy)
+    Wt = mod.tracker_post_linear.weight.reshape(3, 4, 4, 4, 4, 768).mean((2, 4)).reshape(48, 768)
+    assert (feat @ Wt.t() + pk.head_b[:48] - ref).abs().max() < 1e-5
+    assert torch.equal(pk.head_w[48:51].float(), mod.flag_post_linear.weight.to(torch.bfloat16).float())
+    assert pk.head_w[51:].abs().max() == 0
+
+
+def test_merged_temporal_projection_is_algebraically_exact(net):
+    mod = net.seeker
+    blk = mod.tracker_backbone.timesformer.model.blocks[3]
+    with torch.no_grad():
+        blk.temporal_fc.weight.normal_(0, 0.02); blk.temporal_fc.bias.normal_(0, 0.02)
+        blk.temporal_attn.proj.bias.normal_(0, 0.02)
+    o = torch.randn(7, 768, dtype=torch.float64)
+    ref = F.linear(F.linear(o, blk.temporal_attn.proj.weight.double(), blk.temporal_attn.proj.bias.double()),
+                   blk.temporal_fc.weight.double(), blk.temporal_fc.bias.double())
+    W = blk.temporal_fc.weight.double() @ blk.temporal_attn.proj.weight.double()
+    b = blk.temporal_fc.weight.double() @ blk.temporal_attn.proj.bias.double() + blk.temporal_fc.bias.double()
+    assert (F.linear(o, W, b) - ref).abs().max() < 1e-12
+    pk = SeekerEngine(mod)._pack(mod, torch.device('cpu'))
+    assert (pk.blocks[3].t_out[0].double() - W).abs().max() < 2e-4       # one bf16 rounding of |W| ~ 0.02

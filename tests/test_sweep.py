@@ -1,0 +1,57 @@
+"""Sharding of the inference sweep (config 3) incl. a world_size-2 gloo run on CPU."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tcow_b200 import sweep
+
+
+def test_clip_strides_match_reference_rule():
+    # demo/teaduck2.mp4: 200 frames, query at frame 15, T=30, query_time=0 -> strides 1..6
+    assert sweep.clip_strides(200, 30, 15) == [(15, s) for s in range(1, 7)]
+    assert sweep.clip_strides(30, 30, 0) == [(0, 1)]
+    assert sweep.clip_strides(29, 30, 0) == []
+    # seeker_query_time > 0 shifts the clip start before the query frame (data_utils.py:325)
+    assert sweep.clip_strides(200, 30, 20, query_time=2)[:2] == [(18, 1), (16, 2)]
+
+
+def test_shard_partitions_everything_once():
+    items = sweep.plan_sweep(num_videos=3, num_queries=4, num_video_frames=200, num_frames=30, query_idx=15)
+    assert len(items) == 3 * 6 * 4
+    for world in (1, 2, 4, 8):
+        parts = [sweep.shard(items, r, world) for r in range(world)]
+        assert sorted(sum(parts, []), key=items.index) == items
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert [len(b) for b in sweep.batches(items[:10], 4)] == [4, 4, 2]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    items = sweep.plan_sweep(2, 4, 200, 30, 15)
+    mine = sweep.shard(items, rank, world)
+    local = {(it.video, it.query, it.frame_stride): float(it.video * 100 + it.query * 10 + it.frame_stride)
+             for it in mine}
+    # max-over-ranks timing reduction used by bench.py
+    t = torch.tensor([1.0 + rank])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    merged = sweep.gather_to_rank0(local)
+    if rank == 0:
+        q.put((len(merged), float(t), sorted(merged) == sorted((i.video, i.query, i.frame_stride) for i in items)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sweep():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    n, tmax, complete = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert n == 48 and tmax == 2.0 and complete
