@@ -45,6 +45,7 @@ class SeekerEngine:
         self._packed = {}      # device index -> (stamp, _Packed)
         self._workspace = {}   # (device index, Bc, shape key) -> dict of tensors
         self.launches = 0      # kernels launched by the last forward (bench.py's gpu_launches)
+        self.profile = None    # set to a list to collect (kind, flops, bytes, start_event, end_event) per launch
 
     # ------------------------------------------------------------------ weights
     @staticmethod
@@ -141,6 +142,23 @@ class SeekerEngine:
                 self._workspace[key] = ws
         return ws
 
+    def _launch(self, kind, fn, *args, flops=0.0, nbytes=0.0):
+        if self.profile is None:
+            fn(*args)
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*args)
+            e1.record()
+            self.profile.append((kind, flops, nbytes, e0, e1))
+        self.launches += 1
+
+    def _gemm(self, kind, a, w, bias, out, epi):
+        M, K = a.shape
+        N = w.shape[0]
+        self._launch(kind, ops.gemm, a, w, bias, out, epi, flops=2.0 * M * N * K,
+                     nbytes=2.0 * (M * K + N * K) + out.element_size() * M * N * (2 if epi == EPI_F32_ADD else 1))
+
     # ------------------------------------------------------------------ forward
     def forward(self, mod, input_frames, query_mask):
         if not input_frames.is_cuda:
@@ -199,49 +217,46 @@ class SeekerEngine:
         X, A, QKV, O, OCLS, LOW = ws['X'], ws['A'], ws['QKV'], ws['O'], ws['OCLS'], ws['LOW']
         H = ws['H'][:R * 4 * D].view(R, 4 * D)
         PM = ws['H'][:M * Kp].view(M, Kp)
-        n = 0
+        L, G = self._launch, self._gemm
         # ---- patch embedding + embeddings (mask_tracker.py:107-108, vit.py:235-241, vision_tf.py:99-138)
-        ops.patch_gather(frames, query, PM, P, bool(mod.tracker_backbone.pretrained))
-        ops.embed_init(X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D)
-        ops.gemm(PM, pk.patch_w, None, X[:M], EPI_F32_ADD)
-        n += 3
+        L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained),
+          nbytes=16.0 * frames[0].numel() / 3 * Bc + 2.0 * M * Kp)
+        L('embed_init', ops.embed_init, X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D, nbytes=4.0 * R * D)
+        G('gemm_patch', PM, pk.patch_w, None, X[:M], EPI_F32_ADD)
         Rs = R if use_cls else M
+        ln_bytes = lambda rows: 6.0 * rows * D
         for w in pk.blocks:
             # temporal attention + temporal_fc + residual (vit.py:169-176); cls rows untouched
-            ops.layernorm(X[:M], w.tn1[0], w.tn1[1], A[:M])
-            ops.gemm(A[:M], w.t_qkv[0], w.t_qkv[1], QKV[:M], EPI_BF16)
-            ops.attn_temporal(QKV, O, Bc * N, T, HEADS, causal_diag)
+            L('ln', ops.layernorm, X[:M], w.tn1[0], w.tn1[1], A[:M], nbytes=ln_bytes(M))
+            G('gemm_qkv', A[:M], w.t_qkv[0], w.t_qkv[1], QKV[:M], EPI_BF16)
+            L('attn_temporal', ops.attn_temporal, QKV, O, Bc * N, T, HEADS, causal_diag,
+              flops=4.0 * Bc * N * HEADS * T * T * 64, nbytes=8.0 * M * D)
             if w.t_out is not None:
-                ops.gemm(O[:M], w.t_out[0], w.t_out[1], X[:M], EPI_F32_ADD)
-                n += 4
+                G('gemm_proj', O[:M], w.t_out[0], w.t_out[1], X[:M], EPI_F32_ADD)
             else:
-                ops.gemm(O[:M], w.t_proj[0], w.t_proj[1], A[:M], EPI_BF16)
-                ops.gemm(A[:M], w.t_fc[0], w.t_fc[1], X[:M], EPI_F32_ADD)
-                n += 5
+                G('gemm_proj', O[:M], w.t_proj[0], w.t_proj[1], A[:M], EPI_BF16)
+                G('gemm_proj', A[:M], w.t_fc[0], w.t_fc[1], X[:M], EPI_F32_ADD)
             # spatial attention + residual (vit.py:179-215); cls is key/query 0 of every frame
-            ops.layernorm(X[:Rs], w.n1[0], w.n1[1], A[:Rs])
-            ops.gemm(A[:Rs], w.s_qkv[0], w.s_qkv[1], QKV[:Rs], EPI_BF16)
-            ops.attn_spatial(QKV, O, OCLS if use_cls else None, Bc, N, T, HEADS, use_cls, M)
-            n += 3
+            L('ln', ops.layernorm, X[:Rs], w.n1[0], w.n1[1], A[:Rs], nbytes=ln_bytes(Rs))
+            G('gemm_qkv', A[:Rs], w.s_qkv[0], w.s_qkv[1], QKV[:Rs], EPI_BF16)
+            S = N + (1 if use_cls else 0)
+            L('attn_spatial', ops.attn_spatial, QKV, O, OCLS if use_cls else None, Bc, N, T, HEADS, use_cls, M,
+              flops=4.0 * Bc * T * HEADS * S * S * 64, nbytes=8.0 * M * D)
             if use_cls:
-                ops.cls_merge(OCLS, O, Bc, T, D, M, 1 if causal == 1 else 0)
-                n += 1
-            ops.gemm(O[:Rs], w.s_proj[0], w.s_proj[1], X[:Rs], EPI_F32_ADD)
+                L('cls_merge', ops.cls_merge, OCLS, O, Bc, T, D, M, 1 if causal == 1 else 0)
+            G('gemm_proj', O[:Rs], w.s_proj[0], w.s_proj[1], X[:Rs], EPI_F32_ADD)
             # MLP on every token incl. cls (vit.py:216)
-            ops.layernorm(X, w.n2[0], w.n2[1], A)
-            ops.gemm(A, w.fc1[0], w.fc1[1], H, EPI_BF16_GELU)
-            ops.gemm(H, w.fc2[0], w.fc2[1], X, EPI_F32_ADD)
-            n += 4
+            L('ln', ops.layernorm, X, w.n2[0], w.n2[1], A, nbytes=ln_bytes(R))
+            G('gemm_fc1', A, w.fc1[0], w.fc1[1], H, EPI_BF16_GELU)
+            G('gemm_fc2', H, w.fc2[0], w.fc2[1], X, EPI_F32_ADD)
         # ---- optional final norm (vision_tf.py:152-153) or plain cast, then head (mask_tracker.py:112-137)
         if mod.norm_embeddings:
-            ops.layernorm(X[:M], pk.norm[0], pk.norm[1], A[:M])
+            L('ln', ops.layernorm, X[:M], pk.norm[0], pk.norm[1], A[:M], nbytes=ln_bytes(M))
         else:
-            ops.layernorm(X[:M], None, None, A[:M])
-        ops.gemm(A[:M], pk.head_w, pk.head_b, LOW, EPI_F32_STORE)
+            L('ln', ops.layernorm, X[:M], None, None, A[:M], nbytes=ln_bytes(M))
+        G('gemm_head', A[:M], pk.head_w, pk.head_b, LOW, EPI_F32_STORE)
         mode = 1 if (mod.track_map_resize == 'nearest' or pk.stride == 1) else 0
-        ops.mask_upsample(LOW, out_mask, Bc, T, Ho, Wo, mod.output_channels, pk.pp, pk.stride, mode)
-        n += 3
+        L('mask_upsample', ops.mask_upsample, LOW, out_mask, Bc, T, Ho, Wo, mod.output_channels, pk.pp, pk.stride,
+          mode, nbytes=4.0 * out_mask.numel())
         if out_flags is not None:
-            ops.flag_mean(LOW, out_flags, Bc, N, T, mod.flag_channels, pk.flag_col0)
-            n += 1
-        self.launches += n
+            L('flag_mean', ops.flag_mean, LOW, out_flags, Bc, N, T, mod.flag_channels, pk.flag_col0)
