@@ -8,8 +8,9 @@
 //   warp 0 (1 lane) : TMA producer   - cp.async.bulk.tensor 2-D loads, SWIZZLE_128B, 128x64 A + BNx64 W / stage
 //   warp 1 (1 lane) : MMA issuer     - tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16; fp32 accum in TMEM
 //   warp 2          : TMEM allocator - 2 accumulator stages x BN columns
-//   warps 4-7       : epilogue       - tcgen05.ld 32x32b -> +bias (-> exact-erf GELU) -> swizzled smem
-//                                      -> TMA store (bf16 / fp32) or TMA reduce-add into the fp32 residual stream
+//   warps 4-7(-11)  : epilogue       - tcgen05.ld 32x32b -> +bias (-> exact-erf GELU) -> swizzled smem
+//                                      -> TMA store (bf16 / fp32) or TMA reduce-add into the fp32 residual stream;
+//                                      every warp runs its own double-buffered staging ring (no CTA barrier)
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), persistent tile loop.
 #include "ptx.cuh"
 #include "tcow_internal.h"
@@ -19,35 +20,60 @@ namespace tcow {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int EPI>
 struct GemmCfg {
+  static constexpr bool OUT_F32 = (EPI == TCOW_EPI_F32_STORE || EPI == TCOW_EPI_F32_ADD);
+  // The GELU epilogue is issue-bound (exact-erf on 128x256 values per tile): give it 8 warps, 4 otherwise.
+  static constexpr int EPI_WARPS = (EPI == TCOW_EPI_BF16_GELU && BN >= 128) ? 8 : 4;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_BYTES = BM * 128;  // staging chunk: 128 rows x 128 bytes
-  static constexpr int NUM_OUT = 2;
+  static constexpr int OUT_WARP_BYTES = 32 * 128;  // per-warp staging chunk: 32 rows x 128 bytes
+  static constexpr int OUT_BYTES = EPI_WARPS * 2 * OUT_WARP_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + NUM_OUT * OUT_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM_MAX = 232448;
+  static constexpr int STAGES_FIT = (SMEM_MAX - 1024 - BAR_BYTES - OUT_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr bool OUT_F32 = (EPI == TCOW_EPI_F32_STORE || EPI == TCOW_EPI_F32_ADD);
   static constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;
-  static constexpr int NCHUNK = BN / CHUNK_COLS;
+  static constexpr int NCHUNK = BN / CHUNK_COLS;             // chunks per tile row
+  static constexpr int COL_GROUPS = EPI_WARPS / 4;           // warps sharing a TMEM lane quarter split the columns
+  static constexpr int CHUNKS_PER_WARP = NCHUNK / COL_GROUPS;
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
-  static_assert(SMEM <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(NCHUNK % COL_GROUPS == 0, "column split");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU() default, vit.py:46) as x * Phi(x) with Phi from the Abramowitz-Stegun 7.1.26
+// erfc approximation (|abs err| < 1.5e-7, i.e. fp32-level; the result is rounded to bf16 afterwards):
+//   Phi(x) = h for x < 0, 1 - h for x >= 0,  h = 0.5 * t*(a1+t*(a2+t*(a3+t*(a4+t*a5)))) * exp(-x^2/2),
+//   t = 1 / (1 + p*|x|/sqrt(2)).  Written on the negative branch without cancellation.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(t, p, 0.5f * 1.421413741f);
+  p = fmaf(t, p, 0.5f * -0.284496736f);
+  p = fmaf(t, p, 0.5f * 0.254829592f);
+  p *= t;
+  const float w = ax * 0.84932180028801904f;  // sqrt(log2(e) / 2): exp(-x^2/2) = 2^(-w^2)
+  const float h = p * exp2f(-w * w);
+  return x * (x < 0.f ? h : 1.0f - h);
+}
 
-template <int BN, int STAGES, int EPI>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GemmCfg<BN, EPI>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
-  using Cfg = GemmCfg<BN, STAGES, EPI>;
+  using Cfg = GemmCfg<BN, EPI>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t s_out = base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bars = s_out + Cfg::NUM_OUT * Cfg::OUT_BYTES;
+  const uint32_t bars = s_out + Cfg::OUT_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
@@ -74,7 +100,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 32 * Cfg::EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -87,39 +113,41 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Roles are warp-uniform: the whole warp runs the loop and waits on the mbarriers; one elected lane issues.
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------ TMA producer
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
+    // ------------------------------------------------ TMA producer
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
           const uint32_t sa = base + s * Cfg::STAGE_BYTES;
           tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, full_bar(s));
           tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * BK, n_blk * BN, full_bar(s));
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-        const int acc = t & 1;
-        const uint32_t aph = (t >> 1) & 1;
-        mbar_wait(tempty_bar(acc), aph ^ 1);
+    // ------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    uint32_t it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      mbar_wait(tempty_bar(acc), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = base + s * Cfg::STAGE_BYTES;
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
@@ -128,16 +156,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in addr>>4 units
             umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          umma_commit(empty_bar(s));                           // frees the smem stage once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
-    // -------------------------------------------------- epilogue (4 warps, one accumulator row per thread)
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = ew * 32 + lane;
-    const bool issuer = (threadIdx.x == 128);
+    // -------------------------------------------------- epilogue: each warp owns 32 accumulator rows (its TMEM
+    // lane quarter) x CHUNKS_PER_WARP column chunks and runs its own staging ring + TMA stores (no CTA barrier).
+    const int ew = warp & 3;
+    const int cg = (warp - 4) >> 2;
+    const uint32_t my_out = s_out + (warp - 4) * 2 * Cfg::OUT_WARP_BYTES;
+    const uint32_t srow = lane * 128;
+    const uint32_t sw = lane & 7;
     uint32_t t = 0, cc = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -147,18 +179,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < Cfg::NCHUNK; ++c, ++cc) {
-        const uint32_t buf = s_out + (cc & 1) * Cfg::OUT_BYTES;
-        if (issuer) tma_wait_group_read<1>();  // the store issued two chunks ago has finished reading `buf`
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int ci = 0; ci < Cfg::CHUNKS_PER_WARP; ++ci, ++cc) {
+        const int c = cg * Cfg::CHUNKS_PER_WARP + ci;
+        const uint32_t buf = my_out + (cc & 1) * Cfg::OUT_WARP_BYTES;
+        if (elect_one()) tma_wait_group_read<1>();  // this warp's store from two chunks ago has drained `buf`
+        __syncwarp();
         const int col0 = n_blk * BN + c * Cfg::CHUNK_COLS;
-        const uint32_t srow = buf + row * 128;
-        const uint32_t sw = (row & 7);
         if constexpr (Cfg::OUT_F32) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_wait();
-          if (c == Cfg::NCHUNK - 1) {
+          if (ci == Cfg::CHUNKS_PER_WARP - 1) {
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
           }
@@ -170,8 +201,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             o.y = __uint_as_float(v[4 * j + 1]) + b.y;
             o.z = __uint_as_float(v[4 * j + 2]) + b.z;
             o.w = __uint_as_float(v[4 * j + 3]) + b.w;
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((j ^ sw) << 4)), "f"(o.x), "f"(o.y),
-                         "f"(o.z), "f"(o.w)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + srow + ((j ^ sw) << 4)), "f"(o.x),
+                         "f"(o.y), "f"(o.z), "f"(o.w)
                          : "memory");
           }
         } else {
@@ -179,7 +210,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_32x32(t_row + c * 64, v0);
           tmem_ld_32x32(t_row + c * 64 + 32, v1);
           tmem_ld_wait();
-          if (c == Cfg::NCHUNK - 1) {
+          if (ci == Cfg::CHUNKS_PER_WARP - 1) {
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
           }
@@ -202,24 +233,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((j ^ sw) << 4)),
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + srow + ((j ^ sw) << 4)),
                          "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])),
                          "r"(pack_bf16(f[6], f[7]))
                          : "memory");
           }
         }
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (issuer) {
+        __syncwarp();
+        if (elect_one()) {
           if constexpr (EPI == TCOW_EPI_F32_ADD)
-            tma_reduce_add_2d(&tmC, buf, col0, m_blk * BM);
+            tma_reduce_add_2d(&tmC, buf, col0, m_blk * BM + ew * 32);
           else
-            tma_store_2d(&tmC, buf, col0, m_blk * BM);
+            tma_store_2d(&tmC, buf, col0, m_blk * BM + ew * 32);
           tma_commit_group();
         }
       }
     }
-    if (issuer) tma_wait_group<0>();
+    __syncwarp();
+    if (elect_one()) tma_wait_group<0>();
   }
 
   tc_fence_before();
@@ -264,16 +296,16 @@ int make_tmap_2d(CUtensorMap* m, bool is_f32, const void* ptr, uint64_t inner, u
   return 0;
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int EPI>
 static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, STAGES, EPI>;
+  using Cfg = GemmCfg<BN, EPI>;
   alignas(64) CUtensorMap tmA, tmB, tmC;
   int rc;
   if ((rc = make_tmap_2d(&tmA, false, A, K, M, lda, BK, BM))) return rc;
   if ((rc = make_tmap_2d(&tmB, false, W, K, N, ldw, BK, BN))) return rc;
-  if ((rc = make_tmap_2d(&tmC, Cfg::OUT_F32, C, N, M, ldc, Cfg::CHUNK_COLS, BM))) return rc;
-  auto kern = gemm_bf16_tn_kernel<BN, STAGES, EPI>;
+  if ((rc = make_tmap_2d(&tmC, Cfg::OUT_F32, C, N, M, ldc, Cfg::CHUNK_COLS, 32))) return rc;
+  auto kern = gemm_bf16_tn_kernel<BN, EPI>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -284,16 +316,16 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
   }
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, 256, Cfg::SMEM, stream>>>(tmA, tmB, tmC, bias, M, N, K);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, tmC, bias, M, N, K);
   return check_launch("gemm_bf16_tn_kernel");
 }
 
 template <int EPI>
 static int dispatch_bn(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream) {
-  if (N % 256 == 0) return launch_gemm<256, 4, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-  if (N % 128 == 0) return launch_gemm<128, 6, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-  return launch_gemm<64, 8, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  if (N % 256 == 0) return launch_gemm<256, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  if (N % 128 == 0) return launch_gemm<128, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  return launch_gemm<64, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
 }
 
 }  // namespace tcow
