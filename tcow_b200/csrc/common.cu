@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <cuda.h>
+
 #include "tcow_internal.h"
 
 namespace tcow {
@@ -29,6 +31,54 @@ int sm_count() {
   int& c = cached[dev & 63];
   if (c == 0) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
   return c > 0 ? c : 148;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Resolved through the runtime so that the library has no link-time dependency on libcuda (it must load on
+// a machine without a driver for the symbol-export test).
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rank-D tensor, dims[0] innermost (contiguous); strides_bytes[i] = byte stride of dim i+1; 128-byte swizzle.
+int make_tmap_nd(void* map, bool is_f32, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(TCOW_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return set_error(TCOW_ERR_ARG, "tensor map: base must be 16-byte aligned");
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (strides_bytes[i] & 15) return set_error(TCOW_ERR_ARG, "tensor map: strides must be multiples of 16 bytes");
+    st[i] = strides_bytes[i];
+  }
+  CUresult r = fn(static_cast<CUtensorMap*>(map), is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  rank, const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(TCOW_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+// 2-D row-major tensor [rows, inner] with a row pitch; box = [box_rows, box_inner].
+int make_tmap_2d(void* map, bool is_f32, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
+                 uint32_t box_inner, uint32_t box_rows) {
+  const uint64_t dims[2] = {inner, rows};
+  const uint64_t strides[1] = {pitch_elems * (is_f32 ? 4u : 2u)};
+  const uint32_t box[2] = {box_inner, box_rows};
+  return make_tmap_nd(map, is_f32, ptr, 2, dims, strides, box);
 }
 
 }  // namespace tcow

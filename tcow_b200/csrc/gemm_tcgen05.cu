@@ -260,42 +260,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D row-major tensor [rows, inner] with a row pitch; box = [box_rows, box_inner]; 128-byte swizzle.
-int make_tmap_2d(CUtensorMap* m, bool is_f32, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
-                 uint32_t box_inner, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return set_error(TCOW_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  const uint64_t es = is_f32 ? 4 : 2;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((pitch_elems * es) & 15))
-    return set_error(TCOW_ERR_ARG, "tensor map: base and row pitch must be 16-byte aligned");
-  cuuint64_t dims[2] = {inner, rows};
-  cuuint64_t strides[1] = {pitch_elems * es};
-  cuuint32_t box[2] = {box_inner, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(TCOW_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-  return 0;
-}
-
 template <int BN, int EPI>
 static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream) {

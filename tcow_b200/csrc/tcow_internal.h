@@ -1,6 +1,7 @@
 // Internal helpers shared by the .cu translation units (error reporting, device queries).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include "../../include/tcow_b200.h"
 
@@ -8,4 +9,11 @@ namespace tcow {
 int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);
 int sm_count();
+int make_tmap_nd(void* map, bool is_f32, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box);
+int make_tmap_2d(void* map, bool is_f32, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
+                 uint32_t box_inner, uint32_t box_rows);
+// tcgen05/TMEM spatial attention (attn_spatial_tc.cu); valid for N + use_cls <= 304.
+int launch_spatial_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N, int T,
+                      int heads, int use_cls, int64_t cls_row0, cudaStream_t stream);
 }  // namespace tcow

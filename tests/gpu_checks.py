@@ -203,6 +203,16 @@ ALL_CHECKS = [
     ('attn_spatial_24_nocls', lambda: check_attn_spatial(1, 24, 5, False)),
     ('attn_spatial_1201', lambda: check_attn_spatial(1, 1200, 2, True)),
     ('attn_spatial_129', lambda: check_attn_spatial(1, 128, 1, True)),
+    ('attn_spatial_128_nocls', lambda: check_attn_spatial(1, 128, 2, False)),
+    ('attn_spatial_128_cls127', lambda: check_attn_spatial(2, 127, 2, True)),
+    ('attn_spatial_256_cls255', lambda: check_attn_spatial(1, 255, 2, True)),
+    ('attn_spatial_257', lambda: check_attn_spatial(1, 256, 2, True)),
+    ('attn_spatial_258', lambda: check_attn_spatial(1, 257, 3, True)),
+    ('attn_spatial_304', lambda: check_attn_spatial(1, 303, 2, True)),
+    ('attn_spatial_304_nocls', lambda: check_attn_spatial(1, 304, 1, False)),
+    ('attn_spatial_305_fallback', lambda: check_attn_spatial(1, 304, 1, True)),
+    ('attn_spatial_1', lambda: check_attn_spatial(3, 1, 2, False)),
+    ('attn_spatial_many_items', lambda: check_attn_spatial(8, 300, 30, True)),
     ('patch_gather', lambda: check_patch_gather(2, 3, 32, 48, False)),
     ('patch_gather_norm', lambda: check_patch_gather(1, 2, 240, 320, True)),
     ('embed_init', lambda: check_embed_init(2, 6, 4)),
