@@ -1,16 +1,20 @@
-// Spatial attention on the 5th-gen tensor cores (tcgen05 + TMEM), persistent, one CTA per SM.
+// Spatial attention on the 5th-gen tensor cores (tcgen05 + TMEM), persistent, TWO CTAs per SM.
 //
 // Work item = (clip b, frame t, head h): full softmax attention over S = N (+1 cls) tokens of head dim 64
 // (vit.py:78-111 as called at vit.py:186 on the tokens assembled at vit.py:179-185).  Per item:
-//   K, V [S,64] bf16 -> smem (TMA 4-D gather of the strided canonical rows, SWIZZLE_128B; cls row appended by
-//                     the producer warp); double buffered across items
-//   per 128-query tile:  Q tile -> smem ring (TMA)                      S = Q K^T  : tcgen05.mma SS, fp32 in TMEM
-//                        softmax : 128 threads, one query row each, two passes over TMEM (max, then exp2/sum),
-//                                  P (bf16) written back over S with tcgen05.st          — no shuffles needed
-//                        O = P V : tcgen05.mma with A = P from TMEM, B = V as an MN-major smem operand
-//                        O / l  -> bf16 -> canonical output rows (cls query -> out_cls fp32)
+//   K, V [S,64] bf16 -> smem (TMA 4-D gather of the strided canonical rows, SWIZZLE_128B; the cls row is
+//                     appended by the producer warp)
+//   per 128-query tile:  Q tile -> smem ring (TMA); keys in (up to) two blocks A = [0,160), B = [160,S16):
+//     S_x = Q K_x^T   : tcgen05.mma SS, fp32 accumulator in TMEM columns [0,160)
+//     softmax         : 128 threads, one query row each, straight out of TMEM (pipelined tcgen05.ld); running
+//                       max / sum in registers; P (bf16) written back over the consumed S columns (tcgen05.st);
+//                       block B rescales O in TMEM by 2^(m_old-m_new) only when the max moved (online softmax)
+//     O (+)= P_x V_x  : tcgen05.mma with A = P from TMEM, B = V as an MN-major smem operand, O in columns [160,224)
+//     O / l -> bf16 -> canonical output rows (cls query -> out_cls fp32)
+// The two CTAs resident on one SM interleave: while one runs its softmax (MUFU-bound: 16 exp2/clk/SM) the other's
+// MMAs, TMA loads and output stores proceed.  256 TMEM columns and ~110 KB of shared memory per CTA.
 // Warps: 0 TMA producer (+cls rows), 1 MMA issuer, 2 TMEM allocator, 4-7 softmax/epilogue.
-// TMEM: S/P columns [0,320), O columns [320,384).   Limits: S <= 304 (else the mma.sync kernel is used).
+// Limits: S <= 304 (else the mma.sync flash kernel in attention.cu is used).
 #include <math.h>
 
 #include "ptx.cuh"
@@ -18,13 +22,14 @@
 
 namespace tcow {
 
-constexpr int SP_ROWS = 304;                  // K/V rows per stage (S rounded up to 16)
+constexpr int SP_ROWS = 304;                  // K/V rows (S rounded up to 16)
 constexpr int SP_KV_BYTES = SP_ROWS * 128;    // 38912 (multiple of 1024)
-constexpr int SP_STAGE_BYTES = 2 * SP_KV_BYTES;
 constexpr int SP_QTILE_BYTES = 128 * 128;
-constexpr int SP_QSLOTS = 3;
-constexpr int SP_SMEM = 2 * SP_STAGE_BYTES + SP_QSLOTS * SP_QTILE_BYTES + 256 + 1024;
-constexpr int SP_TMEM_O = 320;
+constexpr int SP_QSLOTS = 2;
+constexpr int SP_SMEM = 2 * SP_KV_BYTES + SP_QSLOTS * SP_QTILE_BYTES + 256 + 1024;
+constexpr int SP_BLOCK_A = 160;               // keys in the first block (TMEM S columns)
+constexpr int SP_TMEM_O = 160;                // O accumulator columns [160, 224)
+constexpr int SP_TMEM_COLS = 256;
 
 struct SpatialArgs {
   const __nv_bfloat16* qkv;
@@ -43,23 +48,60 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(256, 1)
+// max over the valid entries of one 32-column chunk (keys key0 .. key0+31, valid if < S)
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int key0, int S, float mx) {
+  if (key0 + 32 <= S) {
+    float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      m0 = fmaxf(m0, __uint_as_float(v[e]));
+      m1 = fmaxf(m1, __uint_as_float(v[e + 1]));
+      m2 = fmaxf(m2, __uint_as_float(v[e + 2]));
+      m3 = fmaxf(m3, __uint_as_float(v[e + 3]));
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  }
+#pragma unroll
+  for (int e = 0; e < 32; ++e)
+    if (key0 + e < S) mx = fmaxf(mx, __uint_as_float(v[e]));
+  return mx;
+}
+
+// p = 2^(s*sc - mxs) for one chunk; packs bf16 pairs into pk; returns the chunk's sum.
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], int key0, int S, float sc,
+                                           float mxs) {
+  float l0 = 0.f, l1 = 0.f;
+  const bool full = (key0 + 32 <= S);
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), sc, -mxs));
+    float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc, -mxs));
+    if (!full) {
+      if (key0 + e >= S) p0 = 0.f;
+      if (key0 + e + 1 >= S) p1 = 0.f;
+    }
+    l0 += p0;
+    l1 += p1;
+    pk[e >> 1] = pack_bf16(p0, p1);
+  }
+  return l0 + l1;
+}
+
+__global__ void __launch_bounds__(256, 2)
 attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid_constant__ CUtensorMap tmQtail,
                        const __grid_constant__ CUtensorMap tmKVfull, const __grid_constant__ CUtensorMap tmKVtail,
                        const SpatialArgs a) {
   extern __shared__ uint8_t smem_sp[];
   const uint32_t raw = smem_u32(smem_sp);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  auto k_buf = [&](int st) { return base + st * SP_STAGE_BYTES; };
-  auto v_buf = [&](int st) { return base + st * SP_STAGE_BYTES + SP_KV_BYTES; };
-  auto q_buf = [&](int slot) { return base + 2 * SP_STAGE_BYTES + slot * SP_QTILE_BYTES; };
-  const uint32_t bars = base + 2 * SP_STAGE_BYTES + SP_QSLOTS * SP_QTILE_BYTES;
-  auto kv_full = [&](int s) { return bars + 8u * s; };
-  auto kv_empty = [&](int s) { return bars + 8u * (2 + s); };
-  auto q_full = [&](int s) { return bars + 8u * (4 + s); };
-  auto q_empty = [&](int s) { return bars + 8u * (7 + s); };
-  const uint32_t s_full = bars + 8u * 10, p_full = bars + 8u * 11, o_full = bars + 8u * 12;
-  const uint32_t tmem_slot = bars + 8u * 13;
+  const uint32_t k_buf = base, v_buf = base + SP_KV_BYTES;
+  auto q_buf = [&](int slot) { return base + 2 * SP_KV_BYTES + slot * SP_QTILE_BYTES; };
+  const uint32_t bars = base + 2 * SP_KV_BYTES + SP_QSLOTS * SP_QTILE_BYTES;
+  const uint32_t kv_full = bars, kv_empty = bars + 8;
+  auto q_full = [&](int s) { return bars + 16u + 8u * s; };
+  auto q_empty = [&](int s) { return bars + 32u + 8u * s; };
+  const uint32_t s_full = bars + 48, p_full = bars + 56, o_full = bars + 64;
+  const uint32_t tmem_slot = bars + 72;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_sp + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,7 +111,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
   const int nq = (S + 127) >> 7;
   const int D = heads * 64;
   const int items = a.B * T * heads;
-  const int n1 = S16 < 256 ? S16 : 256, n2 = S16 - n1;
+  const int n_a = S16 < SP_BLOCK_A ? S16 : SP_BLOCK_A, n_b = S16 - n_a;  // key blocks (multiples of 16)
   const int kv_full_rows = N < 256 ? N : 256, kv_tail_rows = N - kv_full_rows;
 
   if (warp == 0 && lane == 0) {
@@ -79,10 +121,8 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     prefetch_tmap(&tmKVtail);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
-    }
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
     for (int s = 0; s < SP_QSLOTS; ++s) {
       mbar_init(q_full(s), 1);
       mbar_init(q_empty(s), 1);
@@ -93,15 +133,16 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, SP_TMEM_COLS);
     tmem_relinquish();
   }
-  // Rows [S, 304) of every K/V stage are never written by TMA: zero them once (P is 0 there, V must be finite).
-  for (int idx = threadIdx.x; idx < (SP_ROWS - S) * 8 * 4; idx += blockDim.x) {
-    const int bufi = idx / ((SP_ROWS - S) * 8), rem = idx % ((SP_ROWS - S) * 8);
+  // Rows [S, 304) of K/V are never written by TMA: zero them once (P is 0 there, V must be finite).
+  for (int idx = threadIdx.x; idx < (SP_ROWS - S) * 8 * 2; idx += blockDim.x) {
+    const int which = idx / ((SP_ROWS - S) * 8), rem = idx % ((SP_ROWS - S) * 8);
     const int row = S + (rem >> 3), chunk = rem & 7;
-    const uint32_t b0 = (bufi & 1) ? v_buf(bufi >> 1) : k_buf(bufi >> 1);
-    asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(b0 + row * 128 + ((chunk ^ (row & 7)) << 4)), "r"(0) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"((which ? v_buf : k_buf) + row * 128 + ((chunk ^ (row & 7)) << 4)),
+                 "r"(0)
+                 : "memory");
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -114,23 +155,22 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     uint32_t kv_it = 0, q_it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++kv_it) {
       const int h = item % heads, t = (item / heads) % T, b = item / (heads * T);
-      const int st = kv_it & 1;
-      mbar_wait(kv_empty(st), ((kv_it >> 1) & 1) ^ 1);
+      mbar_wait(kv_empty, (kv_it & 1) ^ 1);
       if (a.use_cls && lane < 16) {  // cls k / v rows -> row N of the K / V tiles
         const int which = lane >> 3, chunk = lane & 7;
         const uint4 v = *reinterpret_cast<const uint4*>(a.qkv + (a.cls_row0 + b) * a.ld_qkv + (1 + which) * D + h * 64 + chunk * 8);
-        const uint32_t dst = (which ? v_buf(st) : k_buf(st)) + N * 128 + ((chunk ^ (N & 7)) << 4);
+        const uint32_t dst = (which ? v_buf : k_buf) + N * 128 + ((chunk ^ (N & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (elect_one()) {
-        mbar_expect_tx(kv_full(st), 2u * N * 128u);
-        tma_load_4d(k_buf(st), &tmKVfull, D + h * 64, t, 0, b, kv_full(st));
-        tma_load_4d(v_buf(st), &tmKVfull, 2 * D + h * 64, t, 0, b, kv_full(st));
+        mbar_expect_tx(kv_full, 2u * N * 128u);
+        tma_load_4d(k_buf, &tmKVfull, D + h * 64, t, 0, b, kv_full);
+        tma_load_4d(v_buf, &tmKVfull, 2 * D + h * 64, t, 0, b, kv_full);
         if (kv_tail_rows > 0) {
-          tma_load_4d(k_buf(st) + 256 * 128, &tmKVtail, D + h * 64, t, 256, b, kv_full(st));
-          tma_load_4d(v_buf(st) + 256 * 128, &tmKVtail, 2 * D + h * 64, t, 256, b, kv_full(st));
+          tma_load_4d(k_buf + 256 * 128, &tmKVtail, D + h * 64, t, 256, b, kv_full);
+          tma_load_4d(v_buf + 256 * 128, &tmKVtail, 2 * D + h * 64, t, 256, b, kv_full);
         }
       }
       __syncwarp();
@@ -159,41 +199,55 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_s1 = umma_idesc_bf16(128, n1);
-    const uint32_t idesc_s2 = umma_idesc_bf16(128, n2 > 0 ? n2 : 16);
+    const uint32_t idesc_a = umma_idesc_bf16(128, n_a);
+    const uint32_t idesc_b = umma_idesc_bf16(128, n_b > 0 ? n_b : 16);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
-    uint32_t kv_it = 0, q_it = 0;
+    const uint64_t kd_a = umma_desc_k_sw128(k_buf), kd_b = umma_desc_k_sw128(k_buf + SP_BLOCK_A * 128);
+    const uint64_t vd_a = umma_desc_mn_sw128(v_buf, 1024), vd_b = umma_desc_mn_sw128(v_buf + SP_BLOCK_A * 128, 1024);
+    uint32_t kv_it = 0, q_it = 0, p_ct = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++kv_it) {
-      const int st = kv_it & 1;
-      mbar_wait(kv_full(st), (kv_it >> 1) & 1);
+      mbar_wait(kv_full, kv_it & 1);
       for (int j = 0; j < nq; ++j, ++q_it) {
         const int slot = q_it % SP_QSLOTS;
         mbar_wait(q_full(slot), (q_it / SP_QSLOTS) & 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t qd = umma_desc_k_sw128(q_buf(slot));
-          const uint64_t kd = umma_desc_k_sw128(k_buf(st));
+        const uint64_t qd = umma_desc_k_sw128(q_buf(slot));
+        if (elect_one()) {  // S_a = Q K_a^T
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, qd + 2u * k, kd + 2u * k, idesc_s1, k > 0 ? 1u : 0u);
-          if (n2 > 0) {
-            const uint64_t kd2 = umma_desc_k_sw128(k_buf(st) + 256 * 128);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256, qd + 2u * k, kd2 + 2u * k, idesc_s2, k > 0 ? 1u : 0u);
-          }
-          umma_commit(q_empty(slot));
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, qd + 2u * k, kd_a + 2u * k, idesc_a, k > 0 ? 1u : 0u);
+          if (n_b == 0) umma_commit(q_empty(slot));
           umma_commit(s_full);
         }
         __syncwarp();
-        mbar_wait(p_full, q_it & 1);
+        mbar_wait(p_full, p_ct & 1);
+        ++p_ct;
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t vd = umma_desc_mn_sw128(v_buf(st), 1024);
-          for (int kk = 0; kk < (S16 >> 4); ++kk)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
-            umma_bf16_ts(tmem_base + SP_TMEM_O, tmem_base + 8u * kk, vd + 128u * kk, idesc_o, kk > 0 ? 1u : 0u);
-          umma_commit(o_full);
-          if (j == nq - 1) umma_commit(kv_empty(st));
+        if (elect_one()) {  // O = P_a V_a ; then S_b = Q K_b^T (in order behind it: P_a is consumed first)
+          for (int kk = 0; kk < (n_a >> 4); ++kk)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
+            umma_bf16_ts(tmem_base + SP_TMEM_O, tmem_base + 8u * kk, vd_a + 128u * kk, idesc_o, kk > 0 ? 1u : 0u);
+          if (n_b > 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, qd + 2u * k, kd_b + 2u * k, idesc_b, k > 0 ? 1u : 0u);
+            umma_commit(q_empty(slot));
+            umma_commit(s_full);
+          } else {
+            umma_commit(o_full);
+            if (j == nq - 1) umma_commit(kv_empty);
+          }
         }
         __syncwarp();
+        if (n_b > 0) {
+          mbar_wait(p_full, p_ct & 1);
+          ++p_ct;
+          tc_fence_after();
+          if (elect_one()) {  // O += P_b V_b
+            for (int kk = 0; kk < (n_b >> 4); ++kk)
+              umma_bf16_ts(tmem_base + SP_TMEM_O, tmem_base + 8u * kk, vd_b + 128u * kk, idesc_o, 1u);
+            umma_commit(o_full);
+            if (j == nq - 1) umma_commit(kv_empty);
+          }
+          __syncwarp();
+        }
       }
     }
   } else if (warp >= 4) {
@@ -201,71 +255,92 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int nchunk = (S16 + 31) >> 5;
     const float sc = a.scale_log2;
-    uint32_t tile_ct = 0;
+    uint32_t s_ct = 0, o_ct = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int h = item % heads, t = (item / heads) % T, b = item / (heads * T);
-      for (int j = 0; j < nq; ++j, ++tile_ct) {
+      for (int j = 0; j < nq; ++j, ++o_ct) {
         const int tok = 128 * j + row;
         const bool valid = tok < S;
-        mbar_wait(s_full, tile_ct & 1);
-        tc_fence_after();
-        // pass 1: row maximum
-        float mx = -INFINITY;
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_lane + 32 * c, v);
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int blk = 0; blk < (n_b > 0 ? 2 : 1); ++blk, ++s_ct) {
+          const int key_base = blk ? SP_BLOCK_A : 0;
+          const int nchunk = ((blk ? n_b : n_a) + 31) >> 5;
+          mbar_wait(s_full, s_ct & 1);
+          tc_fence_after();
+          uint32_t va[32], vb[32], pk[16];
+          // ---- pass 1: block maximum (TMEM loads software-pipelined one chunk ahead)
+          float mx = m_run;
+          tmem_ld_32x32(t_lane, va);
           tmem_ld_wait();
-          if (valid) {
-            if (32 * c + 32 <= S) {
+          for (int c = 0; c < nchunk; c += 2) {
+            if (c + 1 < nchunk) tmem_ld_32x32(t_lane + 32 * (c + 1), vb);
+            if (valid) mx = chunk_max(va, key_base + 32 * c, S, mx);
+            tmem_ld_wait();
+            if (c + 1 < nchunk) {
+              if (c + 2 < nchunk) tmem_ld_32x32(t_lane + 32 * (c + 2), va);
+              if (valid) mx = chunk_max(vb, key_base + 32 * (c + 1), S, mx);
+              tmem_ld_wait();
+            }
+          }
+          // ---- online-softmax correction of O (block B only, and only if the running max moved)
+          const float mxs = valid ? mx * sc : 0.f;
+          if (blk == 1) {
+            const float alpha = valid ? ex2_approx((m_run - mx) * sc) : 1.f;
+            l_run *= alpha;
+            if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+              for (int hh = 0; hh < 2; ++hh) {
+                tmem_ld_32x32(t_lane + SP_TMEM_O + 32 * hh, va);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pk[e] = __float_as_uint(__uint_as_float(va[e]) * alpha);
+                tmem_st_32x16(t_lane + SP_TMEM_O + 32 * hh, pk);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pk[e] = __float_as_uint(__uint_as_float(va[16 + e]) * alpha);
+                tmem_st_32x16(t_lane + SP_TMEM_O + 32 * hh + 16, pk);
+              }
+            }
+          }
+          m_run = mx;
+          // ---- pass 2: p = 2^(s*sc - mx*sc), row sum, P (bf16) over the S columns already consumed
+          tmem_ld_32x32(t_lane, va);
+          tmem_ld_wait();
+          for (int c = 0; c < nchunk; c += 2) {
+            if (c + 1 < nchunk) tmem_ld_32x32(t_lane + 32 * (c + 1), vb);
+            if (valid) {
+              l_run += chunk_exp(va, pk, key_base + 32 * c, S, sc, mxs);
             } else {
 #pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (32 * c + e < S) mx = fmaxf(mx, __uint_as_float(v[e]));
+              for (int e = 0; e < 16; ++e) pk[e] = 0u;
             }
-          }
-        }
-        // pass 2: p = 2^(s*sc - mx*sc), row sum, P (bf16) over the S columns already consumed
-        const float mxs = valid ? mx * sc : 0.f;
-        float l = 0.f;
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t v[32], pk[16];
-          tmem_ld_32x32(t_lane + 32 * c, v);
-          tmem_ld_wait();
-          if (valid) {
-            const bool full = (32 * c + 32 <= S);
+            tmem_ld_wait();  // chunk c+1 is in registers before P chunk c overwrites columns [16c, 16c+16)
+            tmem_st_32x16(t_lane + 16 * c, pk);
+            if (c + 1 < nchunk) {
+              if (c + 2 < nchunk) tmem_ld_32x32(t_lane + 32 * (c + 2), va);
+              if (valid) {
+                l_run += chunk_exp(vb, pk, key_base + 32 * (c + 1), S, sc, mxs);
+              } else {
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), sc, -mxs));
-              float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc, -mxs));
-              if (!full) {
-                if (32 * c + e >= S) p0 = 0.f;
-                if (32 * c + e + 1 >= S) p1 = 0.f;
+                for (int e = 0; e < 16; ++e) pk[e] = 0u;
               }
-              l += p0 + p1;
-              pk[e >> 1] = pack_bf16(p0, p1);
+              tmem_ld_wait();
+              tmem_st_32x16(t_lane + 16 * (c + 1), pk);
             }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) pk[e] = 0u;
           }
-          tmem_st_32x16(t_lane + 16 * c, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(p_full);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(p_full);
-        // O
-        mbar_wait(o_full, tile_ct & 1);
+        // ---- O / l -> global
+        mbar_wait(o_full, o_ct & 1);
         tc_fence_after();
         uint32_t o0[32], o1[32];
         tmem_ld_32x32(t_lane + SP_TMEM_O, o0);
         tmem_ld_32x32(t_lane + SP_TMEM_O + 32, o1);
         tmem_ld_wait();
         if (valid) {
-          const float inv = 1.0f / l;
+          const float inv = 1.0f / l_run;
           if (a.use_cls && tok == N) {
             float4* dst = reinterpret_cast<float4*>(a.out_cls + (static_cast<int64_t>(b) * T + t) * D + h * 64);
 #pragma unroll
@@ -296,7 +371,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, SP_TMEM_COLS);
 }
 
 // 4-D view of the patch rows of qkv: (column, t, n, b) -> ((b*N+n)*T+t)*ld + column; box = 64 columns x box_n tokens.
@@ -330,7 +405,8 @@ int launch_spatial_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out
   SpatialArgs a{static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<__nv_bfloat16*>(out), ld_out, out_cls,
                 B, N, T, heads, use_cls, cls_row0, 0.125f * 1.4426950408889634f};
   const int items = B * T * heads;
-  const int grid = items < sm_count() ? items : sm_count();
+  const int slots = 2 * sm_count();
+  const int grid = items < slots ? items : slots;
   attn_spatial_tc_kernel<<<grid, 256, SP_SMEM, stream>>>(tmQf, tmQt, tmKVf, tmKVt, a);
   return check_launch("attn_spatial_tc_kernel");
 }
