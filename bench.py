@@ -150,6 +150,8 @@ def run_ours(args):
     net.load_state_dict(synth.make_state_dict(901, num_frames=T, frame_height=HF, frame_width=WF))
     net = net.to(dev).eval()
     eng = net.seeker.engine()
+    if args.chunk > 0:
+        eng.max_chunk = args.chunk
     B = args.batch
     # 3 queries per video (README.md:42): clips come in triples sharing the RGB and differing in the query.
     rgb_l, q_l = [], []
@@ -279,6 +281,7 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--chunk', type=int, default=0, help='clips per engine pass (0 = engine default)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     if args.impl == 'reference':

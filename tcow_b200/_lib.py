@@ -7,7 +7,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtcow_b200.so')
+# TCOW_B200_LIB selects an alternative build of the same ABI (A/B experiments); default is the in-tree library.
+LIB_PATH = os.environ.get('TCOW_B200_LIB') or os.path.join(_HERE, 'libtcow_b200.so')
 
 TCOW_ERR_ARG, TCOW_ERR_CUDA, TCOW_ERR_ARCH = -1, -2, -3
 EPI_BF16, EPI_BF16_GELU, EPI_F32_STORE, EPI_F32_ADD = 0, 1, 2, 3

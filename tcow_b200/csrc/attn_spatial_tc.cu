@@ -16,6 +16,7 @@
 // Warps: 0 TMA producer (+cls rows), 1 MMA issuer, 2 TMEM allocator, 4-7 softmax/epilogue.
 // Limits: S <= 304 (else the mma.sync flash kernel in attention.cu is used).
 #include <math.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "tcow_internal.h"
@@ -40,6 +41,7 @@ struct SpatialArgs {
   int B, N, T, heads, use_cls;
   int64_t cls_row0;
   float scale_log2;
+  long long* prof;  // SP_PROFILE builds only
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -205,11 +207,20 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     const uint64_t kd_a = umma_desc_k_sw128(k_buf), kd_b = umma_desc_k_sw128(k_buf + SP_BLOCK_A * 128);
     const uint64_t vd_a = umma_desc_mn_sw128(v_buf, 1024), vd_b = umma_desc_mn_sw128(v_buf + SP_BLOCK_A * 128, 1024);
     uint32_t kv_it = 0, q_it = 0, p_ct = 0;
+#ifdef SP_PROFILE
+    long long macc[3] = {0, 0, 0};
+    long long mt;
+#define SP_T0 mt = clock64();
+#define SP_T1(i) macc[i] += clock64() - mt;
+#else
+#define SP_T0
+#define SP_T1(i)
+#endif
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++kv_it) {
-      mbar_wait(kv_full, kv_it & 1);
+      SP_T0 mbar_wait(kv_full, kv_it & 1); SP_T1(0)
       for (int j = 0; j < nq; ++j, ++q_it) {
         const int slot = q_it % SP_QSLOTS;
-        mbar_wait(q_full(slot), (q_it / SP_QSLOTS) & 1);
+        SP_T0 mbar_wait(q_full(slot), (q_it / SP_QSLOTS) & 1); SP_T1(1)
         tc_fence_after();
         const uint64_t qd = umma_desc_k_sw128(q_buf(slot));
         if (elect_one()) {  // S_a = Q K_a^T
@@ -219,7 +230,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
           umma_commit(s_full);
         }
         __syncwarp();
-        mbar_wait(p_full, p_ct & 1);
+        SP_T0 mbar_wait(p_full, p_ct & 1); SP_T1(2)
         ++p_ct;
         tc_fence_after();
         if (elect_one()) {  // O = P_a V_a ; then S_b = Q K_b^T (in order behind it: P_a is consumed first)
@@ -237,7 +248,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
         }
         __syncwarp();
         if (n_b > 0) {
-          mbar_wait(p_full, p_ct & 1);
+          SP_T0 mbar_wait(p_full, p_ct & 1); SP_T1(2)
           ++p_ct;
           tc_fence_after();
           if (elect_one()) {  // O += P_b V_b
@@ -250,6 +261,12 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
         }
       }
     }
+#ifdef SP_PROFILE
+    if (lane == 0 && a.prof && blockIdx.x < 512) {
+      long long* d = a.prof + blockIdx.x * 16;
+      d[8] = macc[0]; d[9] = macc[1]; d[10] = macc[2];
+    }
+#endif
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + output (one query row per thread)
     const int quarter = warp & 3;
@@ -257,6 +274,10 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sc = a.scale_log2;
     uint32_t s_ct = 0, o_ct = 0;
+#ifdef SP_PROFILE
+    long long pacc[4] = {0, 0, 0, 0};
+    const long long tstart = clock64();
+#endif
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int h = item % heads, t = (item / heads) % T, b = item / (heads * T);
       for (int j = 0; j < nq; ++j, ++o_ct) {
@@ -266,8 +287,15 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
         for (int blk = 0; blk < (n_b > 0 ? 2 : 1); ++blk, ++s_ct) {
           const int key_base = blk ? SP_BLOCK_A : 0;
           const int nchunk = ((blk ? n_b : n_a) + 31) >> 5;
+#ifdef SP_PROFILE
+          long long t0 = clock64();
+#endif
           mbar_wait(s_full, s_ct & 1);
           tc_fence_after();
+#ifdef SP_PROFILE
+          long long t1 = clock64();
+          pacc[0] += t1 - t0;
+#endif
           uint32_t va[32], vb[32], pk[16];
           // ---- pass 1: block maximum (TMEM loads software-pipelined one chunk ahead)
           float mx = m_run;
@@ -331,10 +359,20 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(p_full);
+#ifdef SP_PROFILE
+          pacc[1] += clock64() - t1;
+#endif
         }
         // ---- O / l -> global
+#ifdef SP_PROFILE
+        long long t2 = clock64();
+#endif
         mbar_wait(o_full, o_ct & 1);
         tc_fence_after();
+#ifdef SP_PROFILE
+        long long t3 = clock64();
+        pacc[2] += t3 - t2;
+#endif
         uint32_t o0[32], o1[32];
         tmem_ld_32x32(t_lane + SP_TMEM_O, o0);
         tmem_ld_32x32(t_lane + SP_TMEM_O + 32, o1);
@@ -365,10 +403,24 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
             }
           }
         }
+#ifdef SP_PROFILE
+        pacc[3] += clock64() - t3;
+#endif
       }
     }
+#ifdef SP_PROFILE
+    if (warp == 4 && lane == 0 && a.prof && blockIdx.x < 512) {
+      long long* d = a.prof + blockIdx.x * 16;
+      d[0] = pacc[0]; d[1] = pacc[1]; d[2] = pacc[2]; d[3] = pacc[3]; d[4] = clock64() - tstart;
+    }
+#endif
   }
 
+#ifdef SP_PROFILE
+  if (warp == 4 && lane == 0 && a.prof && blockIdx.x < 512) {
+    // filled below via sp_prof_* shared variables
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, SP_TMEM_COLS);
@@ -403,11 +455,35 @@ int launch_spatial_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out
     configured[dev & 63] = true;
   }
   SpatialArgs a{static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<__nv_bfloat16*>(out), ld_out, out_cls,
-                B, N, T, heads, use_cls, cls_row0, 0.125f * 1.4426950408889634f};
+                B, N, T, heads, use_cls, cls_row0, 0.125f * 1.4426950408889634f, nullptr};
+#ifdef SP_PROFILE
+  static long long* dprof = nullptr;
+  if (!dprof) cudaMalloc(&dprof, 16 * 8 * 512);
+  cudaMemsetAsync(dprof, 0, 16 * 8 * 512, stream);
+  a.prof = dprof;
+#endif
   const int items = B * T * heads;
   const int slots = 2 * sm_count();
-  const int grid = items < slots ? items : slots;
+  int grid = items < slots ? items : slots;
+#ifdef SP_PROFILE
+  if (const char* e = getenv("TCOW_SP_GRID")) grid = atoi(e);
+#endif
   attn_spatial_tc_kernel<<<grid, 256, SP_SMEM, stream>>>(tmQf, tmQt, tmKVf, tmKVt, a);
+#ifdef SP_PROFILE
+  {
+    static int calls = 0;
+    if (++calls == 5) {
+      cudaStreamSynchronize(stream);
+      static long long h[16 * 512];
+      cudaMemcpy(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost);
+      double acc[16] = {0};
+      for (int c = 0; c < grid && c < 512; ++c) for (int k = 0; k < 16; ++k) acc[k] += (double)h[c * 16 + k];
+      const int n = grid < 512 ? grid : 512;
+      printf("SP_PROFILE per CTA avg cycles: total %.0f | softmax warp: wait_s %.0f compute %.0f wait_o %.0f epilogue %.0f | mma warp: wait_kv %.0f wait_q %.0f wait_p %.0f\n",
+             acc[4] / n, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[8] / n, acc[9] / n, acc[10] / n);
+    }
+  }
+#endif
   return check_launch("attn_spatial_tc_kernel");
 }
 
