@@ -200,19 +200,41 @@ def run_ours(args):
         # ---------------------------------------------------------- end to end through Seeker.forward with host buffers
         res_h = torch.empty((B, T, 3), dtype=torch.float32).pin_memory()
         area_h = torch.empty((B, 3, T), dtype=torch.float32).pin_memory()
-        def e2e_step():
-            r = rgb_h.to(dev, non_blocking=True)
-            q = q_h.to(dev, non_blocking=True)
-            mask, flags = net(r, q)
-            res_h.copy_(flags, non_blocking=True)
-            area_h.copy_((mask > 0).float().mean(dim=(3, 4)), non_blocking=True)   # per-frame mask area (the metric read back)
-            torch.cuda.current_stream().synchronize()
-        for _ in range(min(args.warmup, 3)):
-            e2e_step()
+        # Inputs start in pinned host memory every step; a copy stream uploads step i+1 while step i computes
+        # (what a DataLoader with pin_memory + non_blocking does); the step's result is read back to the host.
+        copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream()
+        bufs = [(torch.empty_like(rgb_d), torch.empty_like(q_d)) for _ in range(2)]
+        ev_ready = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):
+            k = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[k])
+                bufs[k][0].copy_(rgb_h, non_blocking=True)
+                bufs[k][1].copy_(q_h, non_blocking=True)
+                ev_ready[k].record(copy_stream)
+
+        def e2e_run(n):
+            for k in range(2):
+                ev_free[k].record(cur)
+            upload(0)
+            for i in range(n):
+                if i + 1 < n:
+                    upload(i + 1)
+                k = i & 1
+                cur.wait_event(ev_ready[k])
+                mask, flags = net(bufs[k][0], bufs[k][1])
+                ev_free[k].record(cur)
+                res_h.copy_(flags, non_blocking=True)
+                area_h.copy_((mask > 0).float().mean(dim=(3, 4)), non_blocking=True)   # per-frame mask area read back
+                cur.synchronize()
+
+        e2e_run(min(args.warmup, 3))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         barrier()
         e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
 

@@ -68,7 +68,8 @@ int tcow_attn_temporal(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_ou
  * full softmax attention over [cls(b) ; patches n=0..N-1 of frame t] (use_cls=1) or the patches only
  * (use_cls=0, causal_attention >= 2 or -1, vit.py:202-208).  Patch rows are read/written in place in the
  * canonical layout (row (b*N+n)*T+t — no transposes); the cls q/k/v come from row cls_row0 + b of qkv.
- * The cls query's output for every (b,t) goes to out_cls [B,T,heads*64] fp32. */
+ * The cls query's output for every (b,t) goes to out_cls [B,T,heads*64] fp32; the frame-0 value is also written
+ * (bf16) to row cls_row0 + b of `out`, which is all causal_attention==1 needs (vit.py:198). */
 int tcow_attn_spatial(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N,
                       int T, int heads, int use_cls, int64_t cls_row0, void* stream);
 

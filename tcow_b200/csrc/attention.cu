@@ -386,6 +386,8 @@ attn_spatial_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv, __nv_
             float* dc = out_cls + (static_cast<int64_t>(b) * T + t) * D + head * HD + nd * 8 + tq * 2;
             dc[0] = v0;
             dc[1] = v1;
+            if (t == 0)  // frame-0 cls output doubles as the cls input row of the projection (vit.py:198)
+              *reinterpret_cast<uint32_t*>(out + (cls_row0 + b) * ld_out + head * HD + nd * 8 + tq * 2) = pack_bf16(v0, v1);
           }
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw_addr(sQ, row, nd) + tq * 4), "r"(pack_bf16(v0, v1)) : "memory");
         }

@@ -388,6 +388,20 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
               dst[8 + e] = make_float4(__uint_as_float(o1[4 * e]) * inv, __uint_as_float(o1[4 * e + 1]) * inv,
                                        __uint_as_float(o1[4 * e + 2]) * inv, __uint_as_float(o1[4 * e + 3]) * inv);
             }
+            if (t == 0) {  // frame-0 cls output doubles as the cls input row of the projection (vit.py:198)
+              uint4* dc = reinterpret_cast<uint4*>(a.out + (a.cls_row0 + b) * a.ld_out + h * 64);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                dc[e] = make_uint4(pack_bf16(__uint_as_float(o0[8 * e]) * inv, __uint_as_float(o0[8 * e + 1]) * inv),
+                                   pack_bf16(__uint_as_float(o0[8 * e + 2]) * inv, __uint_as_float(o0[8 * e + 3]) * inv),
+                                   pack_bf16(__uint_as_float(o0[8 * e + 4]) * inv, __uint_as_float(o0[8 * e + 5]) * inv),
+                                   pack_bf16(__uint_as_float(o0[8 * e + 6]) * inv, __uint_as_float(o0[8 * e + 7]) * inv));
+                dc[4 + e] = make_uint4(pack_bf16(__uint_as_float(o1[8 * e]) * inv, __uint_as_float(o1[8 * e + 1]) * inv),
+                                       pack_bf16(__uint_as_float(o1[8 * e + 2]) * inv, __uint_as_float(o1[8 * e + 3]) * inv),
+                                       pack_bf16(__uint_as_float(o1[8 * e + 4]) * inv, __uint_as_float(o1[8 * e + 5]) * inv),
+                                       pack_bf16(__uint_as_float(o1[8 * e + 6]) * inv, __uint_as_float(o1[8 * e + 7]) * inv));
+              }
+            }
           } else {
             uint4* dst = reinterpret_cast<uint4*>(a.out + ((static_cast<int64_t>(b) * N + tok) * T + t) * a.ld_out + h * 64);
 #pragma unroll

@@ -9,49 +9,58 @@
 
 namespace tcow {
 
+// One CTA per (clip, channel, frame) image: the (Ho*pp) x (Wo*pp) low-resolution map is first assembled in shared
+// memory (pp contiguous floats per gather), then every thread produces float4 runs of the full-resolution row.
 __global__ void __launch_bounds__(256) mask_upsample_kernel(const float* __restrict__ low, int64_t ld_low,
                                                             float* __restrict__ out, int B, int T, int Ho, int Wo,
                                                             int C, int pp, int stride, int mode) {
+  extern __shared__ float s_img[];
   const int Hl = Ho * pp, Wl = Wo * pp;
   const int Hf = Hl * stride, Wf = Wl * stride;
   const int N = Ho * Wo;
-  const int WV = Wf / 4;
-  const long long total = static_cast<long long>(B) * C * T * Hf * WV;
-  const long long gstride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int img = blockIdx.x;  // ((b*C + c)*T + t)
+  const int t = img % T, c = (img / T) % C, b = img / (T * C);
+  for (int i = threadIdx.x; i < Hl * Wo; i += blockDim.x) {
+    const int ly = i / Wo, pw = i % Wo;
+    const int n = (ly / pp) * Wo + pw;
+    const float* src = low + ((static_cast<int64_t>(b) * N + n) * T + t) * ld_low + (c * pp + (ly % pp)) * pp;
+    float* dst = s_img + ly * Wl + pw * pp;
+    if (pp == 4) {
+      *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
+    } else {
+      for (int j = 0; j < pp; ++j) dst[j] = __ldg(src + j);
+    }
+  }
+  __syncthreads();
   // PyTorch area_pixel_compute_scale(align_corners=True): (in-1)/(out-1), 0 when out == 1.
   const float sy = (Hf > 1) ? static_cast<float>(Hl - 1) / static_cast<float>(Hf - 1) : 0.f;
   const float sx = (Wf > 1) ? static_cast<float>(Wl - 1) / static_cast<float>(Wf - 1) : 0.f;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gstride) {
-    const int xv = static_cast<int>(i % WV);
-    long long r = i / WV;
-    const int y = static_cast<int>(r % Hf); r /= Hf;
-    const int t = static_cast<int>(r % T); r /= T;
-    const int c = static_cast<int>(r % C);
-    const int b = static_cast<int>(r / C);
-    auto fetch = [&](int ly, int lx) -> float {
-      const int n = (ly / pp) * Wo + (lx / pp);
-      const int col = (c * pp + (ly % pp)) * pp + (lx % pp);
-      return __ldg(low + ((static_cast<int64_t>(b) * N + n) * T + t) * ld_low + col);
-    };
+  const int WV = Wf / 4;
+  float4* dst_img = reinterpret_cast<float4*>(out + static_cast<int64_t>(img) * Hf * Wf);
+  for (int i = threadIdx.x; i < Hf * WV; i += blockDim.x) {
+    const int y = i / WV, xv = i % WV;
     float o[4];
     if (mode == 1 || stride == 1) {  // nearest (scale_factor = stride): src = dst / stride
+      const float* r = s_img + (y / stride) * Wl;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = fetch(y / stride, (xv * 4 + e) / stride);
+      for (int e = 0; e < 4; ++e) o[e] = r[(xv * 4 + e) / stride];
     } else {
       const float fy = sy * static_cast<float>(y);
       const int y0 = static_cast<int>(fy);
       const int y1 = y0 + ((y0 < Hl - 1) ? 1 : 0);
       const float wy1 = fy - static_cast<float>(y0), wy0 = 1.f - wy1;
+      const float* r0 = s_img + y0 * Wl;
+      const float* r1 = s_img + y1 * Wl;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float fx = sx * static_cast<float>(xv * 4 + e);
         const int x0 = static_cast<int>(fx);
         const int x1 = x0 + ((x0 < Wl - 1) ? 1 : 0);
         const float wx1 = fx - static_cast<float>(x0), wx0 = 1.f - wx1;
-        o[e] = wy0 * (wx0 * fetch(y0, x0) + wx1 * fetch(y0, x1)) + wy1 * (wx0 * fetch(y1, x0) + wx1 * fetch(y1, x1));
+        o[e] = wy0 * (wx0 * r0[x0] + wx1 * r0[x1]) + wy1 * (wx0 * r1[x0] + wx1 * r1[x1]);
       }
     }
-    __stcs(reinterpret_cast<float4*>(out) + i, make_float4(o[0], o[1], o[2], o[3]));
+    __stcs(dst_img + i, make_float4(o[0], o[1], o[2], o[3]));
   }
 }
 
@@ -80,12 +89,16 @@ extern "C" int tcow_mask_upsample(const float* low, int64_t ld_low, float* out, 
     return set_error(TCOW_ERR_ARG, "mask_upsample: bad argument");
   if ((Wo * pp * stride) % 4) return set_error(TCOW_ERR_ARG, "mask_upsample: frame width must be a multiple of 4");
   if (mode != 0 && mode != 1) return set_error(TCOW_ERR_ARG, "mask_upsample: mode must be 0 (bilinear) or 1 (nearest)");
-  const long long total = static_cast<long long>(B) * C * T * (Ho * pp * stride) * (Wo * pp * stride / 4);
-  long long blocks = (total + 255) / 256;
-  const long long cap = static_cast<long long>(sm_count()) * 32;
-  if (blocks > cap) blocks = cap;
-  mask_upsample_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(low, ld_low, out, B, T, Ho, Wo, C,
-                                                                                            pp, stride, mode);
+  if ((pp == 4) && ((ld_low % 4) || (reinterpret_cast<uintptr_t>(low) & 15)))
+    return set_error(TCOW_ERR_ARG, "mask_upsample: low must be 16-byte aligned with a row pitch multiple of 4");
+  const size_t smem = static_cast<size_t>(Ho) * pp * Wo * pp * sizeof(float);
+  if (smem > 200 * 1024) return set_error(TCOW_ERR_ARG, "mask_upsample: low-resolution map of %zu bytes exceeds shared memory", smem);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mask_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  mask_upsample_kernel<<<B * C * T, 256, smem, static_cast<cudaStream_t>(stream)>>>(low, ld_low, out, B, T, Ho, Wo, C, pp,
+                                                                               stride, mode);
   return check_launch("mask_upsample_kernel");
 }
 

@@ -242,8 +242,8 @@ class SeekerEngine:
             S = N + (1 if use_cls else 0)
             L('attn_spatial', ops.attn_spatial, QKV, O, OCLS if use_cls else None, Bc, N, T, HEADS, use_cls, M,
               flops=4.0 * Bc * T * HEADS * S * S * 64, nbytes=8.0 * M * D)
-            if use_cls:
-                L('cls_merge', ops.cls_merge, OCLS, O, Bc, T, D, M, 1 if causal == 1 else 0)
+            if use_cls and causal == 0:   # mean over frames (vit.py:195); causal==1 takes frame 0, written in-kernel
+                L('cls_merge', ops.cls_merge, OCLS, O, Bc, T, D, M, 0)
             G('gemm_proj', O[:Rs], w.s_proj[0], w.s_proj[1], X[:Rs], EPI_F32_ADD)
             # MLP on every token incl. cls (vit.py:216)
             L('ln', ops.layernorm, X, w.n2[0], w.n2[1], A, nbytes=ln_bytes(R))

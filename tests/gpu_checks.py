@@ -116,6 +116,8 @@ def check_attn_spatial(B, N, T, use_cls, heads=12):
     if use_cls:
         ref_cls = o[:, :, :, 0, :].reshape(B, T, D)
         err_c = (out_cls - ref_cls).abs().max().item()
+        # the frame-0 cls output is also written (bf16) into the cls row of `out`
+        err_c = max(err_c, (out[M:].float() - out_cls[:, 0].to(torch.bfloat16).float()).abs().max().item())
         o = o[:, :, :, 1:, :]
     ref = o.permute(0, 3, 1, 2, 4).reshape(M, D)
     err = (out[:M].float() - ref).abs().max().item()
@@ -220,4 +222,6 @@ ALL_CHECKS = [
     ('mask_upsample_nearest', lambda: check_mask_upsample(1, 2, 2, 3, 4, 1)),
     ('mask_upsample_stride2', lambda: check_mask_upsample(1, 2, 2, 3, 2, 0)),
     ('mask_upsample_stride1', lambda: check_mask_upsample(1, 2, 2, 3, 1, 0)),
+    ('mask_upsample_hires', lambda: check_mask_upsample(1, 2, 30, 40, 4, 0)),
+    ('mask_upsample_stride8', lambda: check_mask_upsample(1, 1, 3, 2, 8, 0)),
 ]
