@@ -69,19 +69,35 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int key0, in
   return mx;
 }
 
-// p = 2^(s*sc - mxs) for one chunk; packs bf16 pairs into pk; returns the chunk's sum.
+// p = 2^(s*sc - mxs) for one chunk; packs bf16 pairs into pk; returns the chunk's sum.  Full chunks use packed
+// fp32x2 FMAs/adds (half the issue slots); the exp2 itself is the MUFU unit (16/clk/SM), the kernel's real bound.
 __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], int key0, int S, float sc,
                                            float mxs) {
+  if (key0 + 32 <= S) {
+    const uint64_t sc2 = f2_pack(sc, sc), nm2 = f2_pack(-mxs, -mxs);
+    uint64_t la = f2_pack(0.f, 0.f), lb = la;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      float x0, x1, x2, x3;
+      f2_unpack(f2_fma(f2_pack_u(v[e], v[e + 1]), sc2, nm2), x0, x1);
+      f2_unpack(f2_fma(f2_pack_u(v[e + 2], v[e + 3]), sc2, nm2), x2, x3);
+      const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+      la = f2_add(la, f2_pack(p0, p1));
+      lb = f2_add(lb, f2_pack(p2, p3));
+      pk[e >> 1] = pack_bf16(p0, p1);
+      pk[(e >> 1) + 1] = pack_bf16(p2, p3);
+    }
+    float s0, s1;
+    f2_unpack(f2_add(la, lb), s0, s1);
+    return s0 + s1;
+  }
   float l0 = 0.f, l1 = 0.f;
-  const bool full = (key0 + 32 <= S);
 #pragma unroll
   for (int e = 0; e < 32; e += 2) {
     float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), sc, -mxs));
     float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc, -mxs));
-    if (!full) {
-      if (key0 + e >= S) p0 = 0.f;
-      if (key0 + e + 1 >= S) p1 = 0.f;
-    }
+    if (key0 + e >= S) p0 = 0.f;
+    if (key0 + e + 1 >= S) p1 = 0.f;
     l0 += p0;
     l1 += p1;
     pk[e >> 1] = pack_bf16(p0, p1);
@@ -275,7 +291,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     const float sc = a.scale_log2;
     uint32_t s_ct = 0, o_ct = 0;
 #ifdef SP_PROFILE
-    long long pacc[4] = {0, 0, 0, 0};
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tstart = clock64();
 #endif
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -303,59 +319,74 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
           tmem_ld_wait();
           for (int c = 0; c < nchunk; c += 2) {
             if (c + 1 < nchunk) tmem_ld_32x32(t_lane + 32 * (c + 1), vb);
-            if (valid) mx = chunk_max(va, key_base + 32 * c, S, mx);
+            mx = chunk_max(va, key_base + 32 * c, S, mx);
             tmem_ld_wait();
             if (c + 1 < nchunk) {
               if (c + 2 < nchunk) tmem_ld_32x32(t_lane + 32 * (c + 2), va);
-              if (valid) mx = chunk_max(vb, key_base + 32 * (c + 1), S, mx);
+              mx = chunk_max(vb, key_base + 32 * (c + 1), S, mx);
               tmem_ld_wait();
             }
           }
-          // ---- online-softmax correction of O (block B only, and only if the running max moved)
-          const float mxs = valid ? mx * sc : 0.f;
+#ifdef SP_PROFILE
+          long long tp1 = clock64();
+          pacc[4] += tp1 - t1;
+#endif
+          // ---- online softmax: when block B raises a row's maximum, O (block A's partial result, in TMEM) is
+          // rescaled by 2^(m_old - m_new).  The exact maximum is kept as the reference (not a lazy threshold): the
+          // dominant probability is then exactly 1.0 in bf16, which measurably tightens the result.
           if (blk == 1) {
-            const float alpha = valid ? ex2_approx((m_run - mx) * sc) : 1.f;
+            const bool moved = valid && (mx > m_run);
+            const float alpha = moved ? ex2_approx((m_run - mx) * sc) : 1.f;
             l_run *= alpha;
-            if (__any_sync(0xffffffffu, alpha != 1.f)) {
+            if (__any_sync(0xffffffffu, moved)) {
+              const uint64_t al2 = f2_pack(alpha, alpha);
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
                 tmem_ld_32x32(t_lane + SP_TMEM_O + 32 * hh, va);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 16; ++e) pk[e] = __float_as_uint(__uint_as_float(va[e]) * alpha);
+                for (int e = 0; e < 16; e += 2) {
+                  float r0, r1;
+                  f2_unpack(f2_mul(f2_pack_u(va[e], va[e + 1]), al2), r0, r1);
+                  pk[e] = __float_as_uint(r0);
+                  pk[e + 1] = __float_as_uint(r1);
+                }
                 tmem_st_32x16(t_lane + SP_TMEM_O + 32 * hh, pk);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) pk[e] = __float_as_uint(__uint_as_float(va[16 + e]) * alpha);
+                for (int e = 0; e < 16; e += 2) {
+                  float r0, r1;
+                  f2_unpack(f2_mul(f2_pack_u(va[16 + e], va[17 + e]), al2), r0, r1);
+                  pk[e] = __float_as_uint(r0);
+                  pk[e + 1] = __float_as_uint(r1);
+                }
                 tmem_st_32x16(t_lane + SP_TMEM_O + 32 * hh + 16, pk);
               }
             }
           }
+#ifdef SP_PROFILE
+          long long tp2 = clock64();
+          pacc[5] += tp2 - tp1;
+#endif
+          const float mxs = mx * sc;  // rows past S compute on stale data; their results are never stored
           m_run = mx;
           // ---- pass 2: p = 2^(s*sc - mx*sc), row sum, P (bf16) over the S columns already consumed
           tmem_ld_32x32(t_lane, va);
           tmem_ld_wait();
           for (int c = 0; c < nchunk; c += 2) {
             if (c + 1 < nchunk) tmem_ld_32x32(t_lane + 32 * (c + 1), vb);
-            if (valid) {
-              l_run += chunk_exp(va, pk, key_base + 32 * c, S, sc, mxs);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) pk[e] = 0u;
-            }
+            l_run += chunk_exp(va, pk, key_base + 32 * c, S, sc, mxs);
             tmem_ld_wait();  // chunk c+1 is in registers before P chunk c overwrites columns [16c, 16c+16)
             tmem_st_32x16(t_lane + 16 * c, pk);
             if (c + 1 < nchunk) {
               if (c + 2 < nchunk) tmem_ld_32x32(t_lane + 32 * (c + 2), va);
-              if (valid) {
-                l_run += chunk_exp(vb, pk, key_base + 32 * (c + 1), S, sc, mxs);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) pk[e] = 0u;
-              }
+              l_run += chunk_exp(vb, pk, key_base + 32 * (c + 1), S, sc, mxs);
               tmem_ld_wait();
               tmem_st_32x16(t_lane + 16 * (c + 1), pk);
             }
           }
+#ifdef SP_PROFILE
+          pacc[6] += clock64() - tp2;
+#endif
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(p_full);
@@ -426,6 +457,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
     if (warp == 4 && lane == 0 && a.prof && blockIdx.x < 512) {
       long long* d = a.prof + blockIdx.x * 16;
       d[0] = pacc[0]; d[1] = pacc[1]; d[2] = pacc[2]; d[3] = pacc[3]; d[4] = clock64() - tstart;
+      d[5] = pacc[4]; d[6] = pacc[5]; d[7] = pacc[6];
     }
 #endif
   }
@@ -493,8 +525,8 @@ int launch_spatial_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out
       double acc[16] = {0};
       for (int c = 0; c < grid && c < 512; ++c) for (int k = 0; k < 16; ++k) acc[k] += (double)h[c * 16 + k];
       const int n = grid < 512 ? grid : 512;
-      printf("SP_PROFILE per CTA avg cycles: total %.0f | softmax warp: wait_s %.0f compute %.0f wait_o %.0f epilogue %.0f | mma warp: wait_kv %.0f wait_q %.0f wait_p %.0f\n",
-             acc[4] / n, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[8] / n, acc[9] / n, acc[10] / n);
+      printf("SP_PROFILE per CTA avg cycles: total %.0f | softmax warp: wait_s %.0f compute %.0f wait_o %.0f epilogue %.0f | mma warp: wait_kv %.0f wait_q %.0f wait_p %.0f | pass1 %.0f rescale %.0f pass2 %.0f\n",
+             acc[4] / n, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[8] / n, acc[9] / n, acc[10] / n, acc[5] / n, acc[6] / n, acc[7] / n);
     }
   }
 #endif
