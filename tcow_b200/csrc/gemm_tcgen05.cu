@@ -12,6 +12,8 @@
 //                                      -> TMA store (bf16 / fp32) or TMA reduce-add into the fp32 residual stream;
 //                                      every warp runs its own double-buffered staging ring (no CTA barrier)
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), persistent tile loop.
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "tcow_internal.h"
 
@@ -63,7 +65,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * (x < 0.f ? h : 1.0f - h);
 }
 
-template <int BN, int EPI>
+// CL = 1: stand-alone CTAs.  CL = 2: clusters of two CTAs working on vertically adjacent 128-row tiles of the same
+// n-block; each CTA fetches half of the shared weight tile and TMA-multicasts it to both, which cuts the L2->SM
+// operand traffic per CTA from 48 KB to 32 KB per k-block (the mainloop's real limiter at ~14 TB/s of L2 reads).
+template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GemmCfg<BN, EPI>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
@@ -85,8 +90,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM;
   const int num_n = N / BN;
-  const int num_tiles = num_m * num_n;
   const int num_kb = K / BK;
+  // Work unit = CL vertically adjacent tiles of one n-block; every CTA of a cluster walks the same unit sequence.
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int num_tiles = ((num_m + CL - 1) / CL) * num_n;   // units
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -96,7 +104,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);   // every CTA of the cluster must have drained the stage before it is refilled
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -110,6 +118,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can land on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -117,8 +126,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+      const int m_blk = (tile / num_n) * CL + crank, n_blk = tile % num_n;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -127,7 +136,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
           const uint32_t sa = base + s * Cfg::STAGE_BYTES;
           tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, full_bar(s));
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * BK, n_blk * BN, full_bar(s));
+          if (CL == 1) {
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * BK, n_blk * BN, full_bar(s));
+          } else {  // my half of the weight tile, delivered to both CTAs (the peer sends the other half)
+            tma_load_2d_mcast(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / CL), &tmB, kb * BK,
+                              n_blk * BN + crank * (BN / CL), full_bar(s), static_cast<uint16_t>((1 << CL) - 1));
+          }
         }
         __syncwarp();
       }
@@ -136,7 +150,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
     uint32_t it = 0, t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++t) {
       const int acc = t & 1;
       const uint32_t aph = (t >> 1) & 1;
       mbar_wait(tempty_bar(acc), aph ^ 1);
@@ -156,7 +170,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in addr>>4 units
             umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));                           // frees the smem stage once these MMAs have read it
+          if (CL == 1) umma_commit(empty_bar(s));              // frees the smem stage once these MMAs have read it
+          else umma_commit_mcast(empty_bar(s), static_cast<uint16_t>((1 << CL) - 1));  // ... in every CTA of the cluster
           if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -171,8 +186,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t srow = lane * 128;
     const uint32_t sw = lane & 7;
     uint32_t t = 0, cc = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++t) {
+      const int m_blk = (tile / num_n) * CL + crank, n_blk = tile % num_n;
       const int acc = t & 1;
       const uint32_t aph = (t >> 1) & 1;
       mbar_wait(tfull_bar(acc), aph);
@@ -256,20 +271,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it or signal its barriers
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------ host side
-template <int BN, int EPI>
+template <int BN, int EPI, int CL>
 static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EPI>;
   alignas(64) CUtensorMap tmA, tmB, tmC;
   int rc;
   if ((rc = make_tmap_2d(&tmA, false, A, K, M, lda, BK, BM))) return rc;
-  if ((rc = make_tmap_2d(&tmB, false, W, K, N, ldw, BK, BN))) return rc;
+  if ((rc = make_tmap_2d(&tmB, false, W, K, N, ldw, BK, BN / CL))) return rc;
   if ((rc = make_tmap_2d(&tmC, Cfg::OUT_F32, C, N, M, ldc, Cfg::CHUNK_COLS, 32))) return rc;
-  auto kern = gemm_bf16_tn_kernel<BN, EPI>;
+  auto kern = gemm_bf16_tn_kernel<BN, EPI, CL>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -278,18 +294,43 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
     if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured[dev & 63] = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * (N / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, tmC, bias, M, N, K);
+  const int num_m = (M + BM - 1) / BM;
+  const int units = ((num_m + CL - 1) / CL) * (N / BN);
+  const int slots = sm_count() / CL;
+  const int grid = CL * (units < slots ? units : slots);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, bias, M, N, K);
+  if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "gemm_bf16_tn_kernel: launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_tn_kernel");
+}
+
+// Clusters of two pay off once there are enough row tiles to keep every SM pair busy; TCOW_GEMM_CLUSTER=1 disables.
+static bool use_cluster(int M) {
+  static const int forced = [] { const char* e = getenv("TCOW_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
+  if (forced == 1) return false;
+  return M > BM * 2;
 }
 
 template <int EPI>
 static int dispatch_bn(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream) {
-  if (N % 256 == 0) return launch_gemm<256, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-  if (N % 128 == 0) return launch_gemm<128, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-  return launch_gemm<64, EPI>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  if (N % 256 == 0) {
+    if (use_cluster(M)) return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+    return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  }
+  if (N % 128 == 0) return launch_gemm<128, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  return launch_gemm<64, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
 }
 
 }  // namespace tcow
