@@ -53,6 +53,25 @@ def check_gemm(M, N, K, epi, seed=0):
     return e, tol, f'gemm M={M} N={N} K={K} epi={epi}{where}'
 
 
+def check_gelu_accuracy():
+    """fc1 epilogue on inputs spanning [-9, 9]: A = identity-like so that the accumulator equals the bias grid."""
+    d = _dev()
+    M, N, K = 256, 3072, 64
+    a = torch.zeros(M, K, device=d, dtype=torch.bfloat16)
+    w = torch.zeros(N, K, device=d, dtype=torch.bfloat16)
+    bias = torch.linspace(-9, 9, N, device=d)
+    out = torch.empty(M, N, device=d, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, out, ops.EPI_BF16_GELU)
+    torch.cuda.synchronize()
+    ref = F.gelu(bias.double()).float()
+    got = out[0].float()
+    err = (got - ref.to(torch.bfloat16).float()).abs()
+    # allow one bf16 ulp of the reference value (rounding-boundary flips) plus the documented 3e-6 absolute error
+    tol = ref.abs() * 2.0 ** -7 + 4e-6
+    worst = (err - tol).max().item()
+    return max(worst, 0.0), 0.0, f'gelu epilogue accuracy on [-9,9]: max err {err.max().item():.3e}'
+
+
 def check_layernorm(rows, D=768, affine=True):
     d = _dev()
     g = torch.Generator(device=d).manual_seed(1)
@@ -190,6 +209,7 @@ ALL_CHECKS = [
     ('gemm_big_m', lambda: check_gemm(72008, 768, 768, ops.EPI_F32_ADD)),
     ('gemm_store_256', lambda: check_gemm(640, 512, 192, ops.EPI_F32_STORE)),
     ('gemm_one_row', lambda: check_gemm(1, 768, 768, ops.EPI_BF16)),
+    ('gemm_gelu_accuracy', check_gelu_accuracy),
     ('layernorm', lambda: check_layernorm(9001)),
     ('layernorm_cast', lambda: check_layernorm(333, affine=False)),
     ('layernorm_1024', lambda: check_layernorm(100, 1024)),
