@@ -32,11 +32,18 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_WARP_BYTES = 32 * 128;  // per-warp staging chunk: 32 rows x 128 bytes
-  static constexpr int OUT_BYTES = EPI_WARPS * 2 * OUT_WARP_BYTES;
+  // 4 epilogue warps: double-buffered staging; 8 warps: single-buffered (two warps per scheduler cover each other's
+  // TMA-store drain) so that the mainloop keeps 4 smem stages — with 3 the MMA warp waits on TMA 28 % of the time.
+  static constexpr int OUT_BUFS = (EPI_WARPS == 8) ? 1 : 2;
+  static constexpr int OUT_BYTES = EPI_WARPS * OUT_BUFS * OUT_WARP_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_MAX = 232448;
   static constexpr int STAGES_FIT = (SMEM_MAX - 1024 - BAR_BYTES - OUT_BYTES) / STAGE_BYTES;
+#ifdef GEMM_FORCE_STAGES
+  static constexpr int STAGES = GEMM_FORCE_STAGES;
+#else
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+#endif
   static constexpr int SMEM = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;
@@ -196,7 +203,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // lane quarter) x CHUNKS_PER_WARP column chunks and runs its own staging ring + TMA stores (no CTA barrier).
     const int ew = warp & 3;
     const int cg = (warp - 4) >> 2;
-    const uint32_t my_out = s_out + (warp - 4) * 2 * Cfg::OUT_WARP_BYTES;
+    const uint32_t my_out = s_out + (warp - 4) * Cfg::OUT_BUFS * Cfg::OUT_WARP_BYTES;
     const uint32_t srow = lane * 128;
     const uint32_t sw = lane & 7;
     uint32_t t = 0, cc = 0;
@@ -210,8 +217,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int ci = 0; ci < Cfg::CHUNKS_PER_WARP; ++ci, ++cc) {
         const int c = cg * Cfg::CHUNKS_PER_WARP + ci;
-        const uint32_t buf = my_out + (cc & 1) * Cfg::OUT_WARP_BYTES;
-        if (elect_one()) tma_wait_group_read<1>();  // this warp's store from two chunks ago has drained `buf`
+        const uint32_t buf = my_out + (cc % Cfg::OUT_BUFS) * Cfg::OUT_WARP_BYTES;
+        if (elect_one()) tma_wait_group_read<Cfg::OUT_BUFS - 1>();  // the store that last used `buf` has drained it
         __syncwarp();
         const int col0 = n_blk * BN + c * Cfg::CHUNK_COLS;
         if constexpr (Cfg::OUT_F32) {
