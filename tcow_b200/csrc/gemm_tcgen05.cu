@@ -22,14 +22,17 @@ namespace tcow {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 
-template <int BN, int EPI>
+// CL: 1 = stand-alone CTAs; 2 = cluster of two, weight tile TMA-multicast; 3 = CTA pair (cta_group::2 MMA).
+template <int BN, int EPI, int CL = 1>
 struct GemmCfg {
+  static constexpr bool PAIR = (CL == 3);
+  static constexpr int CSIZE = (CL == 1) ? 1 : 2;   // CTAs per cluster
   static constexpr bool OUT_F32 = (EPI == TCOW_EPI_F32_STORE || EPI == TCOW_EPI_F32_ADD);
   // The GELU epilogue is issue-bound (exact-erf on 128x256 values per tile): give it 8 warps, 4 otherwise.
   static constexpr int EPI_WARPS = (EPI == TCOW_EPI_BF16_GELU && BN >= 128) ? 8 : 4;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // pair mode: each CTA holds half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_WARP_BYTES = 32 * 128;  // per-warp staging chunk: 32 rows x 128 bytes
   // 4 epilogue warps: double-buffered staging; 8 warps: single-buffered (two warps per scheduler cover each other's
@@ -90,11 +93,13 @@ __device__ __forceinline__ uint64_t gelu_erf2(float x0, float x1) {
 // n-block; each CTA fetches half of the shared weight tile and TMA-multicasts it to both, which cuts the L2->SM
 // operand traffic per CTA from 48 KB to 32 KB per k-block (the mainloop's real limiter at ~14 TB/s of L2 reads).
 template <int BN, int EPI, int CL>
-__global__ void __launch_bounds__(GemmCfg<BN, EPI>::THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<BN, EPI, CL>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
-  using Cfg = GemmCfg<BN, EPI>;
+  using Cfg = GemmCfg<BN, EPI, CL>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr bool PAIR = Cfg::PAIR;
+  constexpr int CS = Cfg::CSIZE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -113,9 +118,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_n = N / BN;
   const int num_kb = K / BK;
   // Work unit = CL vertically adjacent tiles of one n-block; every CTA of a cluster walks the same unit sequence.
-  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
-  const int num_tiles = ((num_m + CL - 1) / CL) * num_n;   // units
-  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
+  const int num_tiles = ((num_m + CS - 1) / CS) * num_n;   // units
+  const int unit0 = blockIdx.x / CS, unit_step = gridDim.x / CS;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -125,21 +130,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);   // every CTA of the cluster must have drained the stage before it is refilled
+      // multicast mode: every CTA of the cluster must have drained the stage before anyone refills it;
+      // pair mode: one commit from the leader's MMA warp frees the stage in both CTAs
+      mbar_init(empty_bar(s), CL == 2 ? 2 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 32 * Cfg::EPI_WARPS);
+      mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 32 * Cfg::EPI_WARPS);  // pair: both CTAs' epilogues report to the leader
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can land on them
+  if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can land on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -148,28 +160,36 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------ TMA producer
     uint32_t it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_step) {
-      const int m_blk = (tile / num_n) * CL + crank, n_blk = tile % num_n;
+      const int m_blk = (tile / num_n) * CS + crank, n_blk = tile % num_n;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
           const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+          if (PAIR) {
+            // both CTAs' bytes are counted on the leader's barrier; the leader arms it for the pair
+            if (crank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+            const uint32_t lead_bar = cluster_map_shared(full_bar(s), 0);
+            tma_load_2d_pair(sa, &tmA, kb * BK, m_blk * BM, lead_bar);
+            tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, kb * BK, n_blk * BN + crank * (BN / 2), lead_bar);
+          } else {
+          mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, full_bar(s));
           if (CL == 1) {
             tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * BK, n_blk * BN, full_bar(s));
           } else {  // my half of the weight tile, delivered to both CTAs (the peer sends the other half)
-            tma_load_2d_mcast(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / CL), &tmB, kb * BK,
-                              n_blk * BN + crank * (BN / CL), full_bar(s), static_cast<uint16_t>((1 << CL) - 1));
+            tma_load_2d_mcast(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, kb * BK,
+                              n_blk * BN + crank * (BN / 2), full_bar(s), static_cast<uint16_t>(3));
+          }
           }
         }
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+  } else if (warp == 1 && (!PAIR || crank == 0)) {
+    // ------------------------------------------------ MMA issuer (pair mode: the leader CTA issues for both SMs)
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN);
     uint32_t it = 0, t = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_step, ++t) {
       const int acc = t & 1;
@@ -189,11 +209,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in addr>>4 units
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (CL == 1) umma_commit(empty_bar(s));              // frees the smem stage once these MMAs have read it
-          else umma_commit_mcast(empty_bar(s), static_cast<uint16_t>((1 << CL) - 1));  // ... in every CTA of the cluster
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+          // free the smem stage once these MMAs have read it (in every CTA of the cluster);
+          // on the last k-block also hand the accumulator to the epilogue (of both CTAs in pair mode)
+          if (CL == 1) {
+            umma_commit(empty_bar(s));
+            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          } else if (CL == 2) {
+            umma_commit_mcast(empty_bar(s), static_cast<uint16_t>(3));
+            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          } else {
+            umma_commit_pair(empty_bar(s), static_cast<uint16_t>(3));
+            if (kb == num_kb - 1) umma_commit_pair(tfull_bar(acc), static_cast<uint16_t>(3));
+          }
         }
         __syncwarp();
       }
@@ -208,7 +238,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t sw = lane & 7;
     uint32_t t = 0, cc = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_step, ++t) {
-      const int m_blk = (tile / num_n) * CL + crank, n_blk = tile % num_n;
+      const int m_blk = (tile / num_n) * CS + crank, n_blk = tile % num_n;
       const int acc = t & 1;
       const uint32_t aph = (t >> 1) & 1;
       mbar_wait(tfull_bar(acc), aph);
@@ -227,7 +257,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_wait();
           if (ci == Cfg::CHUNKS_PER_WARP - 1) {
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            if (PAIR) mbar_arrive_cluster(tempty_bar(acc), 0);  // the pair's MMA issuer lives in the leader CTA
+            else mbar_arrive(tempty_bar(acc));
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -248,7 +279,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_wait();
           if (ci == Cfg::CHUNKS_PER_WARP - 1) {
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            if (PAIR) mbar_arrive_cluster(tempty_bar(acc), 0);  // the pair's MMA issuer lives in the leader CTA
+            else mbar_arrive(tempty_bar(acc));
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -292,19 +324,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it or signal its barriers
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (CS > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it or signal its barriers
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host side
 template <int BN, int EPI, int CL>
 static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, EPI>;
+  using Cfg = GemmCfg<BN, EPI, CL>;
+  constexpr int CS = Cfg::CSIZE;
   alignas(64) CUtensorMap tmA, tmB, tmC;
   int rc;
   if ((rc = make_tmap_2d(&tmA, false, A, K, M, lda, BK, BM))) return rc;
-  if ((rc = make_tmap_2d(&tmB, false, W, K, N, ldw, BK, BN / CL))) return rc;
+  if ((rc = make_tmap_2d(&tmB, false, W, K, N, ldw, BK, BN / CS))) return rc;
   if ((rc = make_tmap_2d(&tmC, Cfg::OUT_F32, C, N, M, ldc, Cfg::CHUNK_COLS, 32))) return rc;
   auto kern = gemm_bf16_tn_kernel<BN, EPI, CL>;
   static bool configured[64] = {};
@@ -316,9 +352,9 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
     configured[dev & 63] = true;
   }
   const int num_m = (M + BM - 1) / BM;
-  const int units = ((num_m + CL - 1) / CL) * (N / BN);
-  const int slots = sm_count() / CL;
-  const int grid = CL * (units < slots ? units : slots);
+  const int units = ((num_m + CS - 1) / CS) * (N / BN);
+  const int slots = sm_count() / CS;
+  const int grid = CS * (units < slots ? units : slots);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(Cfg::THREADS);
@@ -326,7 +362,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -336,19 +372,23 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
   return check_launch("gemm_bf16_tn_kernel");
 }
 
-// Clusters of two pay off once there are enough row tiles to keep every SM pair busy; TCOW_GEMM_CLUSTER=1 disables.
-static bool use_cluster(int M) {
+// CTA organisation for the 256-wide tiles: 3 = CTA pairs (cta_group::2, default once there are enough row tiles),
+// 2 = cluster of two with weight multicast, 1 = stand-alone CTAs.  TCOW_GEMM_CLUSTER overrides (experiments).
+static int cluster_mode(int M) {
   static const int forced = [] { const char* e = getenv("TCOW_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
-  if (forced == 1) return false;
-  return M > BM * 2;
+  if (M <= BM * 2) return 1;
+  return forced >= 1 && forced <= 3 ? forced : 3;
 }
 
 template <int EPI>
 static int dispatch_bn(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream) {
   if (N % 256 == 0) {
-    if (use_cluster(M)) return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-    return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+    switch (cluster_mode(M)) {
+      case 3: return launch_gemm<256, EPI, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+      case 2: return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+      default: return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+    }
   }
   if (N % 128 == 0) return launch_gemm<128, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
   return launch_gemm<64, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
