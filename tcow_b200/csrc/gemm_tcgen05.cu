@@ -374,17 +374,20 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
 
 // CTA organisation for the 256-wide tiles: 3 = CTA pairs (cta_group::2, default once there are enough row tiles),
 // 2 = cluster of two with weight multicast, 1 = stand-alone CTAs.  TCOW_GEMM_CLUSTER overrides (experiments).
-static int cluster_mode(int M) {
+static int cluster_mode(int M, int epi) {
   static const int forced = [] { const char* e = getenv("TCOW_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
   if (M <= BM * 2) return 1;
-  return forced >= 1 && forced <= 3 ? forced : 3;
+  if (forced >= 1 && forced <= 3) return forced;
+  // The GELU epilogue is the longest; coupling two CTAs' epilogues to one accumulator hand-off (pair mode) costs
+  // it ~4 % (measured), so it keeps independent CTAs sharing the weight tile by multicast.
+  return epi == TCOW_EPI_BF16_GELU ? 2 : 3;
 }
 
 template <int EPI>
 static int dispatch_bn(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream) {
   if (N % 256 == 0) {
-    switch (cluster_mode(M)) {
+    switch (cluster_mode(M, EPI)) {
       case 3: return launch_gemm<256, EPI, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
       case 2: return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
       default: return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
