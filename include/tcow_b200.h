@@ -81,10 +81,12 @@ int tcow_cls_merge(const float* out_cls, void* out, int64_t ld_out, int B, int T
 /* Patch gather: builds the im2col matrix of the patch-embedding conv with the query mask concatenated as
  * the 4th channel (mask_tracker.py:107-108, vit.py:235-238) in one pass:
  *   P[(b*N+n)*T+t, c*256 + r*16 + w] (bf16) = x4[b,c,t,ph*16+r,pw*16+w],  x4 = cat(frames(3ch), query(1ch))
- * frames [B,3,T,Hf,Wf] fp32, query [B,1,T,Hf,Wf] fp32.  normalize != 0 applies (x-0.45)/0.225 to the RGB
- * channels only (vision_tf.py:81-89). */
+ * query [B,1,T,Hf,Wf] fp32 (the B samples of this call); frames [V,3,T,Hf,Wf] fp32 where sample b reads video
+ * (sample0 + b) / queries_per_video — queries_per_video = 1, sample0 = 0 is the plain one-clip-per-sample case,
+ * > 1 lets the Qs queries of a clip (pipeline.py:134-158) share one copy of its RGB frames.
+ * normalize != 0 applies (x-0.45)/0.225 to the RGB channels only (vision_tf.py:81-89). */
 int tcow_patch_gather(const float* frames, const float* query, void* P, int B, int T, int Hf, int Wf,
-                      int patch, int normalize, void* stream);
+                      int patch, int normalize, int queries_per_video, int sample0, void* stream);
 
 /* Residual-stream initialisation (vision_tf.py:99-138): X[(b*N+n)*T+t,:] = conv_bias + pos_embed[1+n] +
  * time_embed[t];  X[M+b,:] = cls_token + pos_embed[0].  The patch GEMM then accumulates into X. */

@@ -36,6 +36,8 @@ CASES = [
          track_map_resize='nearest', flag_channels=0),
     dict(name='mid_causal1', T=30, Hf=64, Wf=96, samples=[8, 9], causal=1, query_frame=3, lattice=(3, 5)),
     dict(name='full_causal1', T=30, Hf=240, Wf=320, samples=[0, 1], causal=1, lattice=(7, 9)),
+    # more than 304 tokens per frame and more than 32 frames: the long-sequence kernels (config 5 in miniature)
+    dict(name='long_causal0', T=34, Hf=256, Wf=320, samples=[12], causal=0, lattice=(5, 7)),
 ]
 WEIGHT_SEED = 901
 

@@ -13,7 +13,7 @@ namespace tcow {
 // K index = c*P*P + r*P + w (Conv2d weight layout (D, C, P, P) flattened), P % 8 == 0.
 __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ frames, const float* __restrict__ query,
                                                            __nv_bfloat16* __restrict__ Pm, int B, int T, int Hf, int Wf,
-                                                           int P, int normalize) {
+                                                           int P, int normalize, int qpv, int sample0) {
   const int Ho = Hf / P, Wo = Wf / P, N = Ho * Wo;
   const int K = 4 * P * P, KC = K / 8;
   const long long total = static_cast<long long>(B) * N * T * KC;
@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
     const int k = kc * 8;
     const int c = k / (P * P), r = (k / P) % P, w = k % P;
     const int y = (n / Wo) * P + r, x = (n % Wo) * P + w;
-    const float* src = (c < 3) ? frames + (((static_cast<long long>(b) * 3 + c) * T + t) * Hf + y) * Wf + x
+    const int vid = (sample0 + b) / qpv;  // queries of one video share its RGB frames (pipeline.py:134-158)
+    const float* src = (c < 3) ? frames + (((static_cast<long long>(vid) * 3 + c) * T + t) * Hf + y) * Wf + x
                                : query + ((static_cast<long long>(b) * T + t) * Hf + y) * Wf + x;
     float4 v0 = __ldcs(reinterpret_cast<const float4*>(src));
     float4 v1 = __ldcs(reinterpret_cast<const float4*>(src) + 1);
@@ -78,16 +79,17 @@ static int grid_for(long long total, int threads) {
 }  // namespace tcow
 
 extern "C" int tcow_patch_gather(const float* frames, const float* query, void* P, int B, int T, int Hf, int Wf,
-                                 int patch, int normalize, void* stream) {
+                                 int patch, int normalize, int queries_per_video, int sample0, void* stream) {
   using namespace tcow;
-  if (!frames || !query || !P || B <= 0 || T <= 0) return set_error(TCOW_ERR_ARG, "patch_gather: bad argument");
+  if (!frames || !query || !P || B <= 0 || T <= 0 || queries_per_video < 1 || sample0 < 0)
+    return set_error(TCOW_ERR_ARG, "patch_gather: bad argument");
   if (patch % 8 != 0 || Hf % patch != 0 || Wf % patch != 0)
     return set_error(TCOW_ERR_ARG, "patch_gather: frame %dx%d not divisible by patch %d (or patch %% 8 != 0)", Hf, Wf, patch);
   if ((reinterpret_cast<uintptr_t>(frames) & 15) || (reinterpret_cast<uintptr_t>(query) & 15) || (Wf % 4))
     return set_error(TCOW_ERR_ARG, "patch_gather: inputs must be 16-byte aligned, contiguous, width %% 4 == 0");
   const long long total = static_cast<long long>(B) * (Hf / patch) * (Wf / patch) * T * (4 * patch * patch / 8);
   patch_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      frames, query, static_cast<__nv_bfloat16*>(P), B, T, Hf, Wf, patch, normalize);
+      frames, query, static_cast<__nv_bfloat16*>(P), B, T, Hf, Wf, patch, normalize, queries_per_video, sample0);
   return check_launch("patch_gather_kernel");
 }
 

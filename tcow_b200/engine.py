@@ -160,7 +160,9 @@ class SeekerEngine:
                      nbytes=2.0 * (M * K + N * K) + out.element_size() * M * N * (2 if epi == EPI_F32_ADD else 1))
 
     # ------------------------------------------------------------------ forward
-    def forward(self, mod, input_frames, query_mask):
+    def forward(self, mod, input_frames, query_mask, queries_per_video=1):
+        """input_frames (V,3,T,Hf,Wf); query_mask (V*queries_per_video,1,T,Hf,Wf), sample s belongs to video
+        s // queries_per_video.  queries_per_video=1 is the reference's Seeker.forward contract."""
         if not input_frames.is_cuda:
             raise RuntimeError('tcow_b200 runs on a CUDA sm_100 device only; move the module and inputs to '
                                'the GPU (there is no CPU fallback)')
@@ -169,7 +171,8 @@ class SeekerEngine:
                                       'torch.no_grad() (as pipeline.py set_phase("test") does)')
         device = input_frames.device
         bbm = mod.tracker_backbone
-        B, Cin, T, Hf, Wf = input_frames.shape
+        V, Cin, T, Hf, Wf = input_frames.shape
+        B = V * queries_per_video
         if Cin != 3:
             raise RuntimeError(f'expected 3 RGB channels (+1 query channel = in_chans 4), got {Cin}')
         if tuple(query_mask.shape) != (B, 1, T, Hf, Wf):
@@ -202,24 +205,24 @@ class SeekerEngine:
             self.launches = 0
             for b0 in range(0, B, self.max_chunk):
                 b1 = min(B, b0 + self.max_chunk)
-                self._run_chunk(mod, pk, frames[b0:b1], query[b0:b1], out_mask[b0:b1],
+                self._run_chunk(mod, pk, frames, query[b0:b1], out_mask[b0:b1],
                                 None if out_flags is None else out_flags[b0:b1],
-                                N, T, D, P, Ho, Wo, use_cls, causal, causal_diag)
+                                N, T, D, P, Ho, Wo, use_cls, causal, causal_diag, queries_per_video, b0)
         return out_mask, out_flags
 
     def _run_chunk(self, mod, pk, frames, query, out_mask, out_flags, N, T, D, P, Ho, Wo, use_cls, causal,
-                   causal_diag):
-        Bc = frames.shape[0]
+                   causal_diag, qpv=1, sample0=0):
+        Bc = query.shape[0]
         M = Bc * N * T
         R = M + Bc
         Kp = 4 * P * P
-        ws = self._ws(frames.device, Bc, N, T, D, Kp, pk.n_pad)
+        ws = self._ws(query.device, Bc, N, T, D, Kp, pk.n_pad)
         X, A, QKV, O, OCLS, LOW = ws['X'], ws['A'], ws['QKV'], ws['O'], ws['OCLS'], ws['LOW']
         H = ws['H'][:R * 4 * D].view(R, 4 * D)
         PM = ws['H'][:M * Kp].view(M, Kp)
         L, G = self._launch, self._gemm
         # ---- patch embedding + embeddings (mask_tracker.py:107-108, vit.py:235-241, vision_tf.py:99-138)
-        L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained),
+        L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained), qpv, sample0,
           nbytes=16.0 * frames[0].numel() / 3 * Bc + 2.0 * M * Kp)
         L('embed_init', ops.embed_init, X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D, nbytes=4.0 * R * D)
         G('gemm_patch', PM, pk.patch_w, None, X[:M], EPI_F32_ADD)

@@ -82,3 +82,21 @@ class QueryMaskTracker(torch.nn.Module):
         '''
         assert query_mask.shape[1] == 1                         # mask_tracker.py:105
         return self.engine().forward(self, input_frames, query_mask)
+
+    def forward_queries(self, input_frames, query_masks):
+        '''
+        All Qs queries of every clip in one pass — what pipeline.py:134-182 obtains by calling forward() Qs times
+        on the same frames and stacking.  The RGB frames are uploaded / read once per clip, not once per query.
+        :param input_frames (B, 3, T, Hf, Wf) tensor.
+        :param query_masks (B, Qs, 1, T, Hf, Wf) tensor.
+        :return (output_mask (B, Qs, C, T, Hf, Wf), output_flags (B, Qs, T, F) or None).
+        '''
+        assert query_masks.dim() == 6 and query_masks.shape[2] == 1
+        (B, Qs) = query_masks.shape[:2]
+        assert input_frames.shape[0] == B
+        (mask, flags) = self.engine().forward(self, input_frames, query_masks.reshape(B * Qs, *query_masks.shape[2:]),
+                                              queries_per_video=Qs)
+        mask = mask.reshape(B, Qs, *mask.shape[1:])
+        if flags is not None:
+            flags = flags.reshape(B, Qs, *flags.shape[1:])
+        return (mask, flags)

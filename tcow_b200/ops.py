@@ -68,14 +68,18 @@ def cls_merge(out_cls, out, B, T, D, cls_row0, mode):
     _lib.call('tcow_cls_merge', out_cls.data_ptr(), out.data_ptr(), out.stride(0), B, T, D, cls_row0, mode, _stream())
 
 
-def patch_gather(frames, query, out, patch, normalize):
+def patch_gather(frames, query, out, patch, normalize, queries_per_video=1, sample0=0):
+    """frames (V,3,T,H,W), query (B,1,T,H,W); sample b uses video (sample0 + b) // queries_per_video."""
     _chk(frames, torch.float32, 'patch_gather.frames'); _chk(query, torch.float32, 'patch_gather.query')
     _chk(out, torch.bfloat16, 'patch_gather.out')
-    B, C, T, Hf, Wf = frames.shape
+    V, C, T, Hf, Wf = frames.shape
+    B = query.shape[0]
     if C != 3 or tuple(query.shape) != (B, 1, T, Hf, Wf) or not (frames.is_contiguous() and query.is_contiguous()):
-        raise ValueError('patch_gather: frames (B,3,T,H,W) and query (B,1,T,H,W) must be contiguous')
+        raise ValueError('patch_gather: frames (V,3,T,H,W) and query (B,1,T,H,W) must be contiguous')
+    if (sample0 + B - 1) // queries_per_video >= V:
+        raise ValueError('patch_gather: not enough videos for the requested samples')
     _lib.call('tcow_patch_gather', frames.data_ptr(), query.data_ptr(), out.data_ptr(), B, T, Hf, Wf, patch,
-              int(normalize), _stream())
+              int(normalize), int(queries_per_video), int(sample0), _stream())
     return out
 
 

@@ -16,3 +16,8 @@ class Seeker(torch.nn.Module):
 
     def forward(self, *args):
         return self.seeker(*args)
+
+    def forward_queries(self, input_frames, query_masks):
+        '''(B,3,T,Hf,Wf), (B,Qs,1,T,Hf,Wf) -> ((B,Qs,C,T,Hf,Wf), (B,Qs,T,F)): the per-query loop of
+        pipeline.py:134-182 as one batched pass over shared frames.'''
+        return self.seeker.forward_queries(input_frames, query_masks)

@@ -155,6 +155,14 @@ def check_patch_gather(B, T, Hf, Wf, normalize):
     torch.cuda.synchronize()
     f2 = (fr - 0.45) / 0.225 if normalize else fr
     x4 = torch.cat([f2, q], 1)
+    if B % 2 == 0:   # shared-frames addressing: 2 queries per video, second half of the samples
+        out2 = torch.empty_like(out[: out.shape[0] // 2])
+        ops.patch_gather(fr[: B // 2].contiguous(), q[B // 2:].contiguous(), out2, P, normalize, 2, B // 2)
+        torch.cuda.synchronize()
+        x4b = torch.cat([f2[: B // 2][(torch.arange(B // 2, B) // 2).to(fr.device)], q[B // 2:]], 1)
+        refb = x4b.reshape(B // 2, 4, T, Ho, P, Wo, P).permute(0, 3, 5, 2, 1, 4, 6).reshape(-1, 4 * P * P)
+        if not torch.equal(out2.float(), refb.to(torch.bfloat16).float()):
+            return float('inf'), 0.0, 'patch_gather shared-frames addressing mismatch'
     ref = x4.reshape(B, 4, T, Ho, P, Wo, P).permute(0, 3, 5, 2, 1, 4, 6).reshape(B * Ho * Wo * T, 4 * P * P)
     return (out.float() - ref.to(torch.bfloat16).float()).abs().max().item(), 1e-2 if normalize else 0.0, \
         f'patch_gather B={B} T={T} {Hf}x{Wf} norm={normalize}'

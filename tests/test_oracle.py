@@ -7,7 +7,7 @@ from conftest import cached_state_dict, golden_names, load_golden
 from oracle import seeker_oracle
 from tcow_b200 import synth
 
-SMALL = [n for n in golden_names() if n.startswith('small_') or n.startswith('mid_')]
+SMALL = [n for n in golden_names() if n.startswith(('small_', 'mid_', 'long_'))]
 
 
 @pytest.mark.parametrize('name', SMALL)

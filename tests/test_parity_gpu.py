@@ -145,6 +145,23 @@ def test_inputs_not_modified_and_dtype_cast(logger):
     assert torch.equal(m32, m64)
 
 
+def test_forward_queries_equals_per_query_loop(logger):
+    """forward_queries == the reference pipeline's loop over queries on shared frames (pipeline.py:134-182)."""
+    meta = dict(T=4, Hf=32, Wf=48, causal=1)
+    net = build(logger, meta)
+    rgb, _ = synth.make_batch([0, 1], num_frames=4, frame_height=32, frame_width=48)
+    qs = torch.stack([torch.stack([synth.make_clip(100 + 3 * b + k, 4, 32, 48)[1] for k in range(3)]) for b in range(2)])
+    with torch.no_grad():
+        m, f = net.forward_queries(rgb.cuda(), qs.cuda())                      # (2,3,3,T,H,W), (2,3,T,3)
+        net.seeker.engine().max_chunk = 4                                        # chunk boundary inside a video
+        m4, f4 = net.forward_queries(rgb.cuda(), qs.cuda())
+        loop = [net(rgb.cuda(), qs[:, k].cuda()) for k in range(3)]
+    assert tuple(m.shape) == (2, 3, 3, 4, 32, 48) and tuple(f.shape) == (2, 3, 4, 3)
+    for k in range(3):
+        assert torch.equal(m[:, k], loop[k][0]) and torch.equal(f[:, k], loop[k][1])
+    assert torch.equal(m, m4) and torch.equal(f, f4)
+
+
 def test_weight_update_invalidates_packed_cache(logger):
     meta = dict(T=4, Hf=32, Wf=48, causal=1)
     net = build(logger, meta)
