@@ -36,8 +36,11 @@ def _f32(t, device):
 
 
 class SeekerEngine:
-    def __init__(self, tracker, max_chunk=8, merge_temporal_proj=True):
+    def __init__(self, tracker, max_chunk=8, merge_temporal_proj=True, fuse_temporal_qkv=True):
         self.max_chunk = max_chunk
+        # qkv projection + temporal attention as one kernel (the qkv tensor never reaches HBM); False keeps the
+        # two-kernel form (GEMM, then tcow_attn_temporal) — numerically identical, used by the tests.
+        self.fuse_temporal_qkv = fuse_temporal_qkv
         # temporal_fc o temporal_attn.proj has no nonlinearity in between (vit.py:111 -> :174): at inference
         # the two 768x768 linears are pre-multiplied in fp32 into one.
         self.merge_temporal_proj = merge_temporal_proj
@@ -70,6 +73,9 @@ class SeekerEngine:
             w.n1 = (_f32(blk.norm1.weight, device), _f32(blk.norm1.bias, device))
             w.n2 = (_f32(blk.norm2.weight, device), _f32(blk.norm2.bias, device))
             w.t_qkv = (bf(blk.temporal_attn.qkv.weight), _f32(blk.temporal_attn.qkv.bias, device))
+            # head-major regrouping [q_h | k_h | v_h] for the fused qkv + temporal attention kernel
+            perm = torch.arange(3 * D, device=device).reshape(3, HEADS, D // HEADS).permute(1, 0, 2).reshape(-1)
+            w.t_qkv_perm = (w.t_qkv[0][perm].contiguous(), w.t_qkv[1][perm].contiguous())
             Wp, bp = _f32(blk.temporal_attn.proj.weight, device), _f32(blk.temporal_attn.proj.bias, device)
             Wf, bfc = _f32(blk.temporal_fc.weight, device), _f32(blk.temporal_fc.bias, device)
             if self.merge_temporal_proj:
@@ -116,7 +122,7 @@ class SeekerEngine:
         return pk
 
     def packed(self, mod, device):
-        stamp = (self._stamp(mod), self.merge_temporal_proj)
+        stamp = (self._stamp(mod), self.merge_temporal_proj)  # fuse_temporal_qkv needs no repack (both forms are packed)
         with self._lock:
             hit = self._packed.get(device.index)
             if hit is not None and hit[0] == stamp:
@@ -231,9 +237,13 @@ class SeekerEngine:
         for w in pk.blocks:
             # temporal attention + temporal_fc + residual (vit.py:169-176); cls rows untouched
             L('ln', ops.layernorm, X[:M], w.tn1[0], w.tn1[1], A[:M], nbytes=ln_bytes(M))
-            G('gemm_qkv', A[:M], w.t_qkv[0], w.t_qkv[1], QKV[:M], EPI_BF16)
-            L('attn_temporal', ops.attn_temporal, QKV, O, Bc * N, T, HEADS, causal_diag,
-              flops=4.0 * Bc * N * HEADS * T * T * 64, nbytes=8.0 * M * D)
+            if self.fuse_temporal_qkv:
+                L('qkv_tattn', ops.qkv_temporal_attn, A[:M], w.t_qkv_perm[0], w.t_qkv_perm[1], O, Bc * N, T, HEADS,
+                  causal_diag, flops=2.0 * M * 3 * D * D + 4.0 * Bc * N * HEADS * T * T * 64, nbytes=4.0 * M * D)
+            else:
+                G('gemm_qkv', A[:M], w.t_qkv[0], w.t_qkv[1], QKV[:M], EPI_BF16)
+                L('attn_temporal', ops.attn_temporal, QKV, O, Bc * N, T, HEADS, causal_diag,
+                  flops=4.0 * Bc * N * HEADS * T * T * 64, nbytes=8.0 * M * D)
             if w.t_out is not None:
                 G('gemm_proj', O[:M], w.t_out[0], w.t_out[1], X[:M], EPI_F32_ADD)
             else:

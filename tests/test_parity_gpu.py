@@ -104,6 +104,19 @@ def test_unmerged_temporal_projection_path(logger):
     assert (mask.cpu()[:, :, :, ::ly, ::lx] - gmask).abs().max().item() <= TOL_LOGIT
 
 
+def test_fused_and_unfused_temporal_paths_agree_bitwise(logger):
+    """qkv + temporal attention as one kernel == GEMM followed by tcow_attn_temporal (same bf16 roundings)."""
+    meta, gmask, _ = load_golden('mid_causal1')
+    net = build(logger, meta)
+    rgb, q = synth.make_batch(meta['samples'], num_frames=meta['T'], frame_height=meta['Hf'], frame_width=meta['Wf'],
+                              query_frame=meta['query_frame'])
+    with torch.no_grad():
+        m1, f1 = net(rgb.cuda(), q.cuda())
+        net.seeker.engine().fuse_temporal_qkv = False
+        m2, f2 = net(rgb.cuda(), q.cuda())
+    assert torch.equal(m1, m2) and torch.equal(f1, f2)
+
+
 def test_causality_bit_exact(logger):
     """causal_attention=1: frames >= t0 cannot influence outputs before t0 — bit-identical, as in the reference."""
     meta = dict(T=6, Hf=32, Wf=32, causal=1)
