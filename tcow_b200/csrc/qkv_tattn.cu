@@ -1,16 +1,22 @@
-// Fused temporal sub-block front half:  O = TemporalAttention( A W_qkv^T + b )  in ONE kernel.
+// Fused temporal sub-block front half:  O = TemporalAttention( A W_qkv^T + b )  in ONE kernel, all on tcgen05.
 //
 // Replaces, for the temporal branch of Block.forward (vit.py:169-173), the qkv Linear (vit.py:81) AND the whole
 // Attention.forward body (vit.py:82-109, causal mask :93-99) — the 3*D-wide qkv tensor never goes to HBM.
 //
 // A GEMM tile is 128 rows x 192 columns: the rows are `seqs_per_tile` complete temporal sequences of T consecutive
 // token rows (4 x 30 = 120 rows at T=30; rows beyond are padding), the columns are [q | k | v] (64 each) of ONE head
-// (the weight rows are permuted head-major on the host).  Mainloop = the tcgen05/TMA pipeline of gemm_tcgen05.cu
-// (M=128, N=192, fp32 accumulator in TMEM, two accumulator stages).  Epilogue (4 warps): accumulator + bias -> bf16
-// q/k/v tiles in swizzled shared memory -> each warp runs the causal softmax attention of one sequence with
-// mma.sync (attn_frag.cuh; 30x30 problems are far below a tcgen05 tile) -> normalised output rows -> HBM.
-// Numerics are identical to running the two kernels back to back (q, k, v are rounded to bf16 exactly once).
-#include "attn_frag.cuh"
+// (the weight rows are permuted head-major on the host).
+//   mainloop (warps 0/1) : the TMA + tcgen05 pipeline of gemm_tcgen05.cu (M=128, N=192, fp32 accumulators in TMEM x2)
+//   epilogue (warps 4-7) : accumulator + bias -> bf16 q / k / v tiles in swizzled smem (exactly the bytes the unfused
+//                          path would have written to HBM), then one query row per thread:
+//       S = Q K^T  for the whole tile at once (128x128x64, tcgen05 SS; only the T x T diagonal blocks are used —
+//                  the off-diagonal waste is ~0.1 us of tensor time and saves all warp-level MMA work),
+//       masked softmax over the row's own sequence straight out of TMEM, P (bf16, zero off the block) back into TMEM,
+//       O = P V    (128x64x128, tcgen05 with A = P from TMEM, V as an MN-major smem operand), O / l -> HBM.
+//   warp 3 issues the two small attention MMAs so that the mainloop issuer never waits on the epilogue.
+// TMEM: accumulators [0,192) and [192,384), S/P/O [384,512).
+#include <math.h>
+
 #include "ptx.cuh"
 #include "tcow_internal.h"
 
@@ -23,7 +29,8 @@ constexpr int FQ_B_BYTES = FQ_BN * 128;
 constexpr int FQ_STAGE_BYTES = FQ_A_BYTES + FQ_B_BYTES;
 constexpr int FQ_TILE_BYTES = FQ_BM * 128;  // one of the q / k / v staging tiles
 constexpr int FQ_SMEM = FQ_STAGES * FQ_STAGE_BYTES + 3 * FQ_TILE_BYTES + 256 + 1024;
-constexpr int FQ_TMEM_COLS = 512;  // 2 accumulator stages x 192 columns, rounded up to a power of two
+constexpr int FQ_TMEM_COLS = 512;
+constexpr int FQ_TMEM_S = 384;  // S (128 cols) -> P (first 64) and O (last 64)
 
 struct FqArgs {
   const float* bias;      // [heads * 192], permuted like the weights
@@ -33,7 +40,12 @@ struct FqArgs {
   float scale_log2;
 };
 
-template <int T_PAD>
+__device__ __forceinline__ float fq_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(256, 1)
 qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FqArgs a) {
   extern __shared__ uint8_t smem_fq[];
@@ -45,7 +57,9 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto empty_bar = [&](int s) { return bars + 8u * (FQ_STAGES + s); };
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * FQ_STAGES + i); };
   auto tempty_bar = [&](int i) { return bars + 8u * (2 * FQ_STAGES + 2 + i); };
-  const uint32_t tmem_slot = bars + 8u * (2 * FQ_STAGES + 4);
+  const uint32_t qkv_ready = bars + 8u * (2 * FQ_STAGES + 4), s_ready = qkv_ready + 8, p_ready = qkv_ready + 16,
+                 o_ready = qkv_ready + 24;
+  const uint32_t tmem_slot = qkv_ready + 32;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_fq + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,6 +82,10 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 128);
     }
+    mbar_init(qkv_ready, 128);
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_ready, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -97,14 +115,14 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
+    // ------------------------------------------------ mainloop MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(FQ_BM, FQ_BN);
     uint32_t it = 0, t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
       mbar_wait(tempty_bar(acc), ((t >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 256;
+      const uint32_t d_tmem = tmem_base + acc * FQ_BN;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % FQ_STAGES;
         mbar_wait(full_bar(s), (it / FQ_STAGES) & 1);
@@ -121,20 +139,57 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------ attention MMA issuer (S = Q K^T, then O = P V, per tile)
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
+    const uint64_t qd = umma_desc_k_sw128(s_q), kd = umma_desc_k_sw128(s_k), vd = umma_desc_mn_sw128(s_v, 1024);
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      mbar_wait(qkv_ready, t & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + FQ_TMEM_S, qd + 2u * k, kd + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_ready);
+      }
+      __syncwarp();
+      mbar_wait(p_ready, t & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
+          umma_bf16_ts(tmem_base + FQ_TMEM_S + 64, tmem_base + FQ_TMEM_S + 8u * kk, vd + 128u * kk, idesc_o,
+                       kk > 0 ? 1u : 0u);
+        umma_commit(o_ready);
+      }
+      __syncwarp();
+    }
   } else if (warp >= 4) {
-    // ------------------------------------------------ epilogue: q/k/v tile -> smem -> per-sequence attention -> HBM
+    // ------------------------------------------------ epilogue: one accumulator / query row per thread
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
-    const bool live = row < rows_per_tile;  // padding rows are staged as zeros (V must stay finite)
+    const bool live = row < rows_per_tile;   // padding rows are staged as zeros (V must stay finite)
     const uint32_t sw = row & 7;
+    const int sidx = live ? row / T : 0;     // sequence of this row inside the tile
+    const int k0 = sidx * T;                 // its keys are tile rows [k0, k0+T)
+    const int qi = row - k0;                 // position of the query inside its sequence
+    const int kvis = (a.causal_diag < 0 || qi + a.causal_diag + 1 > T) ? T : qi + a.causal_diag + 1;  // visible keys
+    // 32-column chunks of S that hold keys of any row of this warp (warp-uniform)
+    const int w_lo = ((ew * 32) / T) * T, w_hi_row = (ew * 32 + 31 < rows_per_tile ? ew * 32 + 31 : rows_per_tile - 1);
+    const int c_lo = (ew * 32 < rows_per_tile) ? w_lo / 32 : 4;
+    const int c_hi = (ew * 32 < rows_per_tile) ? ((w_hi_row / T) * T + T - 1) / 32 : -1;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    const float sc = a.scale_log2;
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int m_blk = tile / heads, h = tile % heads;
       const int acc = t & 1;
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 256;
+      const uint32_t t_row = t_lane + acc * FQ_BN;
       const float* bias_h = a.bias + h * FQ_BN;
+      // ---- q / k / v (+bias) -> bf16 -> swizzled smem tiles (K-major rows of 128 bytes)
 #pragma unroll 1
       for (int part = 0; part < 3; ++part) {
         const uint32_t dst = (part == 0 ? s_q : (part == 1 ? s_k : s_v)) + row * 128;
@@ -144,7 +199,7 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         if (part == 2) {
           tc_fence_before();
-          mbar_arrive(tempty_bar(acc));  // accumulator drained: the MMA warp may start the tile after next
+          mbar_arrive(tempty_bar(acc));  // accumulator drained: the mainloop may reuse this TMEM stage
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -161,22 +216,73 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                        : "memory");
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the three tiles are complete
-      const int seq0 = m_blk * spt;
-      for (int s = ew; s < spt && seq0 + s < a.num_seq; s += 4) {
-        const int r0 = s * T;
-        temporal_attend_seq<T_PAD>(s_q, s_k, s_v, r0, T, a.causal_diag, a.scale_log2);
-        __nv_bfloat16* dst = a.out + (static_cast<int64_t>(seq0 + s) * T) * a.ld_out + h * HD;
-        for (int idx = lane; idx < T * 8; idx += 32) {
-          const int r = idx >> 3, chunk = idx & 7;
-          uint4 v;
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                       : "r"(sw_addr(s_q, r0 + r, chunk)));
-          *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r) * a.ld_out + chunk * 8) = v;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(qkv_ready);
+      // ---- masked softmax of this row over its own sequence's keys, straight out of TMEM
+      mbar_wait(s_ready, t & 1);
+      tc_fence_after();
+      const uint32_t t_s = t_lane + FQ_TMEM_S;
+      float mx = -INFINITY;
+      for (int c = c_lo; c <= c_hi; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_s + 32 * c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int jl = 32 * c + e - k0;  // key position inside the row's sequence
+          if (jl >= 0 && jl < kvis) mx = fmaxf(mx, __uint_as_float(v[e]));
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the tiles before they are refilled
+      const float mxs = mx * sc;
+      float l = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        if (c >= c_lo && c <= c_hi) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_s + 32 * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const int jl = 32 * c + e - k0;
+            float p0 = fq_ex2(fmaf(__uint_as_float(v[e]), sc, -mxs));
+            float p1 = fq_ex2(fmaf(__uint_as_float(v[e + 1]), sc, -mxs));
+            if (!(live && jl >= 0 && jl < kvis)) p0 = 0.f;
+            if (!(live && jl + 1 >= 0 && jl + 1 < kvis)) p1 = 0.f;
+            l += p0 + p1;
+            pk[e >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[e] = 0u;
+        }
+        tmem_st_32x16(t_s + 16 * c, pk);  // P chunk c over S columns this thread has already consumed
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      // ---- O / l -> bf16 -> HBM (128 contiguous bytes per row)
+      mbar_wait(o_ready, t & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(t_s + 64, o0);
+      tmem_ld_32x32(t_s + 96, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (live && m_blk * spt + sidx < a.num_seq) {
+        const float inv = 1.0f / l;
+        uint4* dst = reinterpret_cast<uint4*>(a.out + (static_cast<int64_t>(m_blk) * rows_per_tile + row) * a.ld_out + h * 64);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          dst[e] = make_uint4(pack_bf16(__uint_as_float(o0[8 * e]) * inv, __uint_as_float(o0[8 * e + 1]) * inv),
+                              pack_bf16(__uint_as_float(o0[8 * e + 2]) * inv, __uint_as_float(o0[8 * e + 3]) * inv),
+                              pack_bf16(__uint_as_float(o0[8 * e + 4]) * inv, __uint_as_float(o0[8 * e + 5]) * inv),
+                              pack_bf16(__uint_as_float(o0[8 * e + 6]) * inv, __uint_as_float(o0[8 * e + 7]) * inv));
+          dst[4 + e] = make_uint4(pack_bf16(__uint_as_float(o1[8 * e]) * inv, __uint_as_float(o1[8 * e + 1]) * inv),
+                                  pack_bf16(__uint_as_float(o1[8 * e + 2]) * inv, __uint_as_float(o1[8 * e + 3]) * inv),
+                                  pack_bf16(__uint_as_float(o1[8 * e + 4]) * inv, __uint_as_float(o1[8 * e + 5]) * inv),
+                                  pack_bf16(__uint_as_float(o1[8 * e + 6]) * inv, __uint_as_float(o1[8 * e + 7]) * inv));
+        }
+      }
     }
   }
 
@@ -185,14 +291,13 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) tmem_dealloc(tmem_base, FQ_TMEM_COLS);
 }
 
-template <int T_PAD>
 static int launch_fq(const void* A, int64_t lda, const void* W, int64_t ldw, const FqArgs& a, int M, cudaStream_t stream) {
   alignas(64) CUtensorMap tmA, tmB;
   int rc;
   const int rows_per_tile = a.seqs_per_tile * a.T;
   if ((rc = make_tmap_2d(&tmA, false, A, a.K, M, lda, FQ_BK, rows_per_tile))) return rc;
   if ((rc = make_tmap_2d(&tmB, false, W, a.K, static_cast<uint64_t>(a.heads) * FQ_BN, ldw, FQ_BK, FQ_BN))) return rc;
-  auto kern = qkv_tattn_kernel<T_PAD>;
+  auto kern = qkv_tattn_kernel;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -218,13 +323,11 @@ extern "C" int tcow_qkv_temporal_attn(const void* A, int64_t lda, const void* Wp
   if (K % 64 != 0) return set_error(TCOW_ERR_ARG, "qkv_temporal_attn: K (%d) must be a multiple of 64", K);
   if ((ld_out % 8) || (reinterpret_cast<uintptr_t>(bias_perm) & 15))
     return set_error(TCOW_ERR_ARG, "qkv_temporal_attn: output pitch must be a multiple of 8, bias 16-byte aligned");
-  const int T_PAD = T <= 32 ? 32 : 64;
-  // every sequence's T_PAD-row window must stay inside the 128-row tile
-  FqArgs a{bias_perm, static_cast<__nv_bfloat16*>(out), ld_out, num_seq, T, heads, K, (128 - T_PAD) / T + 1, causal_diag,
+  // as many whole sequences as fit the 128 accumulator rows
+  FqArgs a{bias_perm, static_cast<__nv_bfloat16*>(out), ld_out, num_seq, T, heads, K, 128 / T, causal_diag,
            0.125f * 1.4426950408889634f};
   const long long M = static_cast<long long>(num_seq) * T;
   if (M > 0x7fffffffLL) return set_error(TCOW_ERR_ARG, "qkv_temporal_attn: too many rows");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (T_PAD == 32) return launch_fq<32>(A, lda, Wperm, ldw, a, static_cast<int>(M), s);
-  return launch_fq<64>(A, lda, Wperm, ldw, a, static_cast<int>(M), s);
+  return launch_fq(A, lda, Wperm, ldw, a, static_cast<int>(M), s);
 }

@@ -104,8 +104,9 @@ def test_unmerged_temporal_projection_path(logger):
     assert (mask.cpu()[:, :, :, ::ly, ::lx] - gmask).abs().max().item() <= TOL_LOGIT
 
 
-def test_fused_and_unfused_temporal_paths_agree_bitwise(logger):
-    """qkv + temporal attention as one kernel == GEMM followed by tcow_attn_temporal (same bf16 roundings)."""
+def test_fused_and_unfused_temporal_paths_agree(logger):
+    """qkv + temporal attention as one kernel vs GEMM followed by tcow_attn_temporal: same bf16 q,k,v, the softmax
+    runs on different units (tcgen05 vs mma.sync), so agreement is to rounding, and both match the reference."""
     meta, gmask, _ = load_golden('mid_causal1')
     net = build(logger, meta)
     rgb, q = synth.make_batch(meta['samples'], num_frames=meta['T'], frame_height=meta['Hf'], frame_width=meta['Wf'],
@@ -114,7 +115,9 @@ def test_fused_and_unfused_temporal_paths_agree_bitwise(logger):
         m1, f1 = net(rgb.cuda(), q.cuda())
         net.seeker.engine().fuse_temporal_qkv = False
         m2, f2 = net(rgb.cuda(), q.cuda())
-    assert torch.equal(m1, m2) and torch.equal(f1, f2)
+    assert (m1 - m2).abs().max().item() <= 2e-3 and (f1 - f2).abs().max().item() <= 5e-3
+    ly, lx = meta['lattice']
+    assert (m2.cpu()[:, :, :, ::ly, ::lx] - gmask).abs().max().item() <= TOL_LOGIT
 
 
 def test_causality_bit_exact(logger):

@@ -18,11 +18,17 @@ qkv = (torch.randn(M + B, 3 * D, device=d, generator=g)).to(torch.bfloat16)
 out = torch.empty(M + B, D, device=d, dtype=torch.bfloat16)
 ocls = torch.empty(B, T, D, device=d)
 x = torch.randn(M + B, D, device=d, generator=g)
+wq = (torch.randn(3 * D, D, device=d, generator=g) * 0.03).to(torch.bfloat16)
+bq = torch.randn(3 * D, device=d, generator=g) * 0.1
+a_ = x[:M].to(torch.bfloat16)
 for _ in range(reps):
     if op == 'spatial':
         ops.attn_spatial(qkv, out, ocls, B, N, T, H, True, M)
     elif op == 'temporal':
         ops.attn_temporal(qkv, out, B * N, T, H, 0)
+    elif op == 'fq':
+        a_ = x[:M].to(torch.bfloat16) if 'a_' not in dir() else a_
+        ops.qkv_temporal_attn(a_, wq, bq, out, B * N, T, H, 0)
     elif op == 'ln':
         gm = torch.ones(D, device=d); bt = torch.zeros(D, device=d)
         ops.layernorm(x, gm, bt, out)
@@ -34,6 +40,8 @@ for _ in range(10):
         ops.attn_spatial(qkv, out, ocls, B, N, T, H, True, M)
     elif op == 'temporal':
         ops.attn_temporal(qkv, out, B * N, T, H, 0)
+    elif op == 'fq':
+        ops.qkv_temporal_attn(a_, wq, bq, out, B * N, T, H, 0)
 e1.record()
 torch.cuda.synchronize()
 print(op, 'avg us', e0.elapsed_time(e1) * 100)
