@@ -14,7 +14,11 @@
 //       masked softmax over the row's own sequence straight out of TMEM, P (bf16, zero off the block) back into TMEM,
 //       O = P V    (128x64x128, tcgen05 with A = P from TMEM, V as an MN-major smem operand), O / l -> HBM.
 //   warp 3 issues the two small attention MMAs so that the mainloop issuer never waits on the epilogue.
-// TMEM: accumulators [0,192) and [192,384), S/P/O [384,512).
+// The epilogue is software-pipelined over three tiles so that the two tensor-pipe round trips of a tile (S, then P V —
+// each queued behind up to three k-blocks of mainloop MMAs) hide behind other tiles' work:
+//   iteration i:  output(i-2)  |  drain accumulator(i) -> q/k/v smem[i&1] -> issue S(i)  |  softmax(i-1) -> issue PV(i-1)
+// TMEM: accumulator [0,192) (drained into registers in one go, so a single stage costs the mainloop ~300 cycles per
+// tile), S/P/O regions [192,320) and [320,448).
 #include <math.h>
 
 #include "ptx.cuh"
@@ -23,14 +27,15 @@
 namespace tcow {
 
 constexpr int FQ_BM = 128, FQ_BN = 192, FQ_BK = 64;
-constexpr int FQ_STAGES = 4;
+constexpr int FQ_STAGES = 3;
 constexpr int FQ_A_BYTES = FQ_BM * 128;
 constexpr int FQ_B_BYTES = FQ_BN * 128;
 constexpr int FQ_STAGE_BYTES = FQ_A_BYTES + FQ_B_BYTES;
 constexpr int FQ_TILE_BYTES = FQ_BM * 128;  // one of the q / k / v staging tiles
-constexpr int FQ_SMEM = FQ_STAGES * FQ_STAGE_BYTES + 3 * FQ_TILE_BYTES + 256 + 1024;
+constexpr int FQ_QKV_BYTES = 3 * FQ_TILE_BYTES;  // one q|k|v staging buffer; two of them (software-pipelined epilogue)
+constexpr int FQ_SMEM = FQ_STAGES * FQ_STAGE_BYTES + 2 * FQ_QKV_BYTES + 256 + 1024;
 constexpr int FQ_TMEM_COLS = 512;
-constexpr int FQ_TMEM_S = 384;  // S (128 cols) -> P (first 64) and O (last 64)
+constexpr int FQ_TMEM_S = 192;  // two S regions of 128 columns: S -> P (first 64) and O (last 64)
 
 struct FqArgs {
   const float* bias;      // [heads * 192], permuted like the weights
@@ -51,15 +56,16 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_fq[];
   const uint32_t raw = smem_u32(smem_fq);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t s_q = base + FQ_STAGES * FQ_STAGE_BYTES, s_k = s_q + FQ_TILE_BYTES, s_v = s_k + FQ_TILE_BYTES;
-  const uint32_t bars = s_v + FQ_TILE_BYTES;
+  const uint32_t s_qkv = base + FQ_STAGES * FQ_STAGE_BYTES;  // buffer b: q at +b*FQ_QKV_BYTES, then k, then v
+  const uint32_t bars = s_qkv + 2 * FQ_QKV_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (FQ_STAGES + s); };
-  auto tfull_bar = [&](int i) { return bars + 8u * (2 * FQ_STAGES + i); };
-  auto tempty_bar = [&](int i) { return bars + 8u * (2 * FQ_STAGES + 2 + i); };
-  const uint32_t qkv_ready = bars + 8u * (2 * FQ_STAGES + 4), s_ready = qkv_ready + 8, p_ready = qkv_ready + 16,
-                 o_ready = qkv_ready + 24;
-  const uint32_t tmem_slot = qkv_ready + 32;
+  const uint32_t tfull_bar = bars + 8u * (2 * FQ_STAGES), tempty_bar = tfull_bar + 8;
+  auto qkv_ready = [&](int b) { return tfull_bar + 16u + 8u * b; };
+  auto s_ready = [&](int b) { return tfull_bar + 32u + 8u * b; };
+  auto p_ready = [&](int b) { return tfull_bar + 48u + 8u * b; };
+  auto o_ready = [&](int b) { return tfull_bar + 64u + 8u * b; };
+  const uint32_t tmem_slot = tfull_bar + 80u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_fq + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,14 +84,14 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 128);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 128);
+      mbar_init(qkv_ready(i), 128);
+      mbar_init(s_ready(i), 1);
+      mbar_init(p_ready(i), 128);
+      mbar_init(o_ready(i), 1);
     }
-    mbar_init(qkv_ready, 128);
-    mbar_init(s_ready, 1);
-    mbar_init(p_ready, 128);
-    mbar_init(o_ready, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -119,10 +125,9 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t idesc = umma_idesc_bf16(FQ_BM, FQ_BN);
     uint32_t it = 0, t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const int acc = t & 1;
-      mbar_wait(tempty_bar(acc), ((t >> 1) & 1) ^ 1);
+      mbar_wait(tempty_bar, (t & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * FQ_BN;
+      const uint32_t d_tmem = tmem_base;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % FQ_STAGES;
         mbar_wait(full_bar(s), (it / FQ_STAGES) & 1);
@@ -134,36 +139,46 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < FQ_BK / 16; ++k)
             umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(s));
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (kb == num_kb - 1) umma_commit(tfull_bar);
         }
         __syncwarp();
       }
     }
   } else if (warp == 3) {
-    // ------------------------------------------------ attention MMA issuer (S = Q K^T, then O = P V, per tile)
+    // ------------------------------------------------ attention MMA issuer: S(j), then P V of the previous tile
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
-    const uint64_t qd = umma_desc_k_sw128(s_q), kd = umma_desc_k_sw128(s_k), vd = umma_desc_mn_sw128(s_v, 1024);
-    uint32_t t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      mbar_wait(qkv_ready, t & 1);
-      tc_fence_after();
-      if (elect_one()) {
+    int n_mine = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) ++n_mine;
+    for (int j = 0; j <= n_mine; ++j) {
+      if (j < n_mine) {
+        const int b = j & 1;
+        mbar_wait(qkv_ready(b), (j >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t qd = umma_desc_k_sw128(s_qkv + b * FQ_QKV_BYTES);
+          const uint64_t kd = umma_desc_k_sw128(s_qkv + b * FQ_QKV_BYTES + FQ_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + FQ_TMEM_S, qd + 2u * k, kd + 2u * k, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_ready);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + FQ_TMEM_S + 128 * b, qd + 2u * k, kd + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(s_ready(b));
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(p_ready, t & 1);
-      tc_fence_after();
-      if (elect_one()) {
+      if (j >= 1) {
+        const int i = j - 1, b = i & 1;
+        mbar_wait(p_ready(b), (i >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = umma_desc_mn_sw128(s_qkv + b * FQ_QKV_BYTES + 2 * FQ_TILE_BYTES, 1024);
+          const uint32_t reg = tmem_base + FQ_TMEM_S + 128 * b;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
-          umma_bf16_ts(tmem_base + FQ_TMEM_S + 64, tmem_base + FQ_TMEM_S + 8u * kk, vd + 128u * kk, idesc_o,
-                       kk > 0 ? 1u : 0u);
-        umma_commit(o_ready);
+          for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
+            umma_bf16_ts(reg + 64, reg + 8u * kk, vd + 128u * kk, idesc_o, kk > 0 ? 1u : 0u);
+          umma_commit(o_ready(b));
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue: one accumulator / query row per thread
@@ -181,107 +196,117 @@ qkv_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int c_hi = (ew * 32 < rows_per_tile) ? ((w_hi_row / T) * T + T - 1) / 32 : -1;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     const float sc = a.scale_log2;
-    uint32_t t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const int m_blk = tile / heads, h = tile % heads;
-      const int acc = t & 1;
-      mbar_wait(tfull_bar(acc), (t >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t_row = t_lane + acc * FQ_BN;
-      const float* bias_h = a.bias + h * FQ_BN;
-      // ---- q / k / v (+bias) -> bf16 -> swizzled smem tiles (K-major rows of 128 bytes)
-#pragma unroll 1
-      for (int part = 0; part < 3; ++part) {
-        const uint32_t dst = (part == 0 ? s_q : (part == 1 ? s_k : s_v)) + row * 128;
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(t_row + part * 64, v0);
-        tmem_ld_32x32(t_row + part * 64 + 32, v1);
+    int n_mine = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) ++n_mine;
+    float l_keep[2] = {1.f, 1.f};  // row sums of the tiles in flight (indexed by tile parity)
+    for (int i = 0; i < n_mine + 2; ++i) {
+      // ---------------- C: output of tile i-2:  O / l -> bf16 -> HBM (128 contiguous bytes per row)
+      if (i >= 2) {
+        const int j = i - 2, b = j & 1;
+        const int tile = blockIdx.x + j * gridDim.x;
+        const int m_blk = tile / heads, h = tile % heads;
+        mbar_wait(o_ready(b), (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(t_lane + FQ_TMEM_S + 128 * b + 64, o0);
+        tmem_ld_32x32(t_lane + FQ_TMEM_S + 128 * b + 96, o1);
         tmem_ld_wait();
-        if (part == 2) {
-          tc_fence_before();
-          mbar_arrive(tempty_bar(acc));  // accumulator drained: the mainloop may reuse this TMEM stage
-        }
+        tc_fence_before();
+        if (live && m_blk * spt + sidx < a.num_seq) {
+          const float inv = 1.0f / l_keep[b];
+          uint4* dst = reinterpret_cast<uint4*>(a.out + (static_cast<int64_t>(m_blk) * rows_per_tile + row) * a.ld_out + h * 64);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t* v = (j < 4) ? (v0 + 8 * j) : (v1 + 8 * (j - 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_h + part * 64) + 2 * j);
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_h + part * 64) + 2 * j + 1);
-          uint32_t p0 = pack_bf16(__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y);
-          uint32_t p1 = pack_bf16(__uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w);
-          uint32_t p2 = pack_bf16(__uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y);
-          uint32_t p3 = pack_bf16(__uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w);
-          if (!live) p0 = p1 = p2 = p3 = 0u;
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + ((j ^ sw) << 4)), "r"(p0), "r"(p1), "r"(p2),
-                       "r"(p3)
-                       : "memory");
+          for (int e = 0; e < 4; ++e) {
+            dst[e] = make_uint4(pack_bf16(__uint_as_float(o0[8 * e]) * inv, __uint_as_float(o0[8 * e + 1]) * inv),
+                                pack_bf16(__uint_as_float(o0[8 * e + 2]) * inv, __uint_as_float(o0[8 * e + 3]) * inv),
+                                pack_bf16(__uint_as_float(o0[8 * e + 4]) * inv, __uint_as_float(o0[8 * e + 5]) * inv),
+                                pack_bf16(__uint_as_float(o0[8 * e + 6]) * inv, __uint_as_float(o0[8 * e + 7]) * inv));
+            dst[4 + e] = make_uint4(pack_bf16(__uint_as_float(o1[8 * e]) * inv, __uint_as_float(o1[8 * e + 1]) * inv),
+                                    pack_bf16(__uint_as_float(o1[8 * e + 2]) * inv, __uint_as_float(o1[8 * e + 3]) * inv),
+                                    pack_bf16(__uint_as_float(o1[8 * e + 4]) * inv, __uint_as_float(o1[8 * e + 5]) * inv),
+                                    pack_bf16(__uint_as_float(o1[8 * e + 6]) * inv, __uint_as_float(o1[8 * e + 7]) * inv));
+          }
         }
       }
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(qkv_ready);
-      // ---- masked softmax of this row over its own sequence's keys, straight out of TMEM
-      mbar_wait(s_ready, t & 1);
-      tc_fence_after();
-      const uint32_t t_s = t_lane + FQ_TMEM_S;
-      float mx = -INFINITY;
-      for (int c = c_lo; c <= c_hi; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + 32 * c, v);
-        tmem_ld_wait();
+      // ---------------- A: drain accumulator of tile i, q / k / v (+bias) -> bf16 -> swizzled smem buffer i&1
+      if (i < n_mine) {
+        const int b = i & 1;
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int h = tile % heads;
+        const float* bias_h = a.bias + h * FQ_BN;
+        mbar_wait(tfull_bar, i & 1);
+        tc_fence_after();
+        uint32_t v[6][32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int jl = 32 * c + e - k0;  // key position inside the row's sequence
-          if (jl >= 0 && jl < kvis) mx = fmaxf(mx, __uint_as_float(v[e]));
+        for (int c = 0; c < 6; ++c) tmem_ld_32x32(t_lane + 32 * c, v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(tempty_bar);  // the whole accumulator row is in registers: the mainloop may start the next tile
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const uint32_t dst = s_qkv + b * FQ_QKV_BYTES + (c >> 1) * FQ_TILE_BYTES + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_h + 32 * c) + 2 * j);
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_h + 32 * c) + 2 * j + 1);
+            uint32_t p0 = pack_bf16(__uint_as_float(v[c][8 * j + 0]) + b0.x, __uint_as_float(v[c][8 * j + 1]) + b0.y);
+            uint32_t p1 = pack_bf16(__uint_as_float(v[c][8 * j + 2]) + b0.z, __uint_as_float(v[c][8 * j + 3]) + b0.w);
+            uint32_t p2 = pack_bf16(__uint_as_float(v[c][8 * j + 4]) + b1.x, __uint_as_float(v[c][8 * j + 5]) + b1.y);
+            uint32_t p3 = pack_bf16(__uint_as_float(v[c][8 * j + 6]) + b1.z, __uint_as_float(v[c][8 * j + 7]) + b1.w);
+            if (!live) p0 = p1 = p2 = p3 = 0u;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + ((((c & 1) * 4 + j) ^ sw) << 4)), "r"(p0),
+                         "r"(p1), "r"(p2), "r"(p3)
+                         : "memory");
+          }
         }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(qkv_ready(b));
       }
-      const float mxs = mx * sc;
-      float l = 0.f;
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-        if (c >= c_lo && c <= c_hi) {
+      // ---------------- B: masked softmax of tile i-1 over the row's own sequence, straight out of TMEM
+      if (i >= 1 && i - 1 < n_mine) {
+        const int j = i - 1, b = j & 1;
+        mbar_wait(s_ready(b), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_s = t_lane + FQ_TMEM_S + 128 * b;
+        float mx = -INFINITY;
+        for (int c = c_lo; c <= c_hi; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(t_s + 32 * c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const int jl = 32 * c + e - k0;
-            float p0 = fq_ex2(fmaf(__uint_as_float(v[e]), sc, -mxs));
-            float p1 = fq_ex2(fmaf(__uint_as_float(v[e + 1]), sc, -mxs));
-            if (!(live && jl >= 0 && jl < kvis)) p0 = 0.f;
-            if (!(live && jl + 1 >= 0 && jl + 1 < kvis)) p1 = 0.f;
-            l += p0 + p1;
-            pk[e >> 1] = pack_bf16(p0, p1);
+          for (int e = 0; e < 32; ++e) {
+            const int jl = 32 * c + e - k0;  // key position inside the row's sequence
+            if (jl >= 0 && jl < kvis) mx = fmaxf(mx, __uint_as_float(v[e]));
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) pk[e] = 0u;
         }
-        tmem_st_32x16(t_s + 16 * c, pk);  // P chunk c over S columns this thread has already consumed
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      // ---- O / l -> bf16 -> HBM (128 contiguous bytes per row)
-      mbar_wait(o_ready, t & 1);
-      tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(t_s + 64, o0);
-      tmem_ld_32x32(t_s + 96, o1);
-      tmem_ld_wait();
-      tc_fence_before();
-      if (live && m_blk * spt + sidx < a.num_seq) {
-        const float inv = 1.0f / l;
-        uint4* dst = reinterpret_cast<uint4*>(a.out + (static_cast<int64_t>(m_blk) * rows_per_tile + row) * a.ld_out + h * 64);
+        const float mxs = mx * sc;
+        float l = 0.f;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+          if (c >= c_lo && c <= c_hi) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_s + 32 * c, v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          dst[e] = make_uint4(pack_bf16(__uint_as_float(o0[8 * e]) * inv, __uint_as_float(o0[8 * e + 1]) * inv),
-                              pack_bf16(__uint_as_float(o0[8 * e + 2]) * inv, __uint_as_float(o0[8 * e + 3]) * inv),
-                              pack_bf16(__uint_as_float(o0[8 * e + 4]) * inv, __uint_as_float(o0[8 * e + 5]) * inv),
-                              pack_bf16(__uint_as_float(o0[8 * e + 6]) * inv, __uint_as_float(o0[8 * e + 7]) * inv));
-          dst[4 + e] = make_uint4(pack_bf16(__uint_as_float(o1[8 * e]) * inv, __uint_as_float(o1[8 * e + 1]) * inv),
-                                  pack_bf16(__uint_as_float(o1[8 * e + 2]) * inv, __uint_as_float(o1[8 * e + 3]) * inv),
-                                  pack_bf16(__uint_as_float(o1[8 * e + 4]) * inv, __uint_as_float(o1[8 * e + 5]) * inv),
-                                  pack_bf16(__uint_as_float(o1[8 * e + 6]) * inv, __uint_as_float(o1[8 * e + 7]) * inv));
+            for (int e = 0; e < 32; e += 2) {
+              const int jl = 32 * c + e - k0;
+              float p0 = fq_ex2(fmaf(__uint_as_float(v[e]), sc, -mxs));
+              float p1 = fq_ex2(fmaf(__uint_as_float(v[e + 1]), sc, -mxs));
+              if (!(live && jl >= 0 && jl < kvis)) p0 = 0.f;
+              if (!(live && jl + 1 >= 0 && jl + 1 < kvis)) p1 = 0.f;
+              l += p0 + p1;
+              pk[e >> 1] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = 0u;
+          }
+          tmem_st_32x16(t_s + 16 * c, pk);  // P chunk c over S columns this thread has already consumed
         }
+        l_keep[b] = l;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready(b));
       }
     }
   }

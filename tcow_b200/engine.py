@@ -16,6 +16,7 @@ attention gathers rows with stride T, every GEMM is row-order agnostic.
 """
 from __future__ import annotations
 
+import os
 import threading
 
 import torch
@@ -40,7 +41,7 @@ class SeekerEngine:
         self.max_chunk = max_chunk
         # qkv projection + temporal attention as one kernel (the qkv tensor never reaches HBM); False keeps the
         # two-kernel form (GEMM, then tcow_attn_temporal) — numerically identical, used by the tests.
-        self.fuse_temporal_qkv = fuse_temporal_qkv
+        self.fuse_temporal_qkv = fuse_temporal_qkv and os.environ.get('TCOW_FUSE_TEMPORAL', '1') != '0'
         # temporal_fc o temporal_attn.proj has no nonlinearity in between (vit.py:111 -> :174): at inference
         # the two 768x768 linears are pre-multiplied in fp32 into one.
         self.merge_temporal_proj = merge_temporal_proj
