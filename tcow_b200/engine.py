@@ -50,6 +50,11 @@ class SeekerEngine:
         self._workspace = {}   # (device index, Bc, shape key) -> dict of tensors
         self.launches = 0      # kernels launched by the last forward (bench.py's gpu_launches)
         self.profile = None    # set to a list to collect (kind, flops, bytes, start_event, end_event) per launch
+        # The ~135 launches between the input gather and the output upsample touch only engine-owned buffers, so they
+        # are captured once per (device, chunk shape, weights) into a CUDA graph and replayed (no launch gaps).
+        self.use_cuda_graph = os.environ.get('TCOW_CUDA_GRAPH', '1') != '0'
+        self._graphs = {}      # key -> (torch.cuda.CUDAGraph, launches) ; key -> int warm-up count in _warm
+        self._warm = {}
 
     # ------------------------------------------------------------------ weights
     @staticmethod
@@ -132,6 +137,7 @@ class SeekerEngine:
             pk = self._pack(mod, device)
         with self._lock:
             self._packed[device.index] = (stamp, pk)
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != device.index}   # they hold the old weights
         return pk
 
     def _ws(self, device, Bc, N, T, D, K_patch, n_pad):
@@ -231,6 +237,40 @@ class SeekerEngine:
         # ---- patch embedding + embeddings (mask_tracker.py:107-108, vit.py:235-241, vision_tf.py:99-138)
         L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained), qpv, sample0,
           nbytes=16.0 * frames[0].numel() / 3 * Bc + 2.0 * M * Kp)
+        # ---- everything from the embeddings to the head GEMM: engine-owned buffers only -> CUDA-graph replay
+        key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, self.fuse_temporal_qkv,
+               bool(mod.norm_embeddings), id(pk))
+        core = lambda: self._core(mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag)
+        if self.use_cuda_graph and self.profile is None:
+            hit = self._graphs.get(key)
+            if hit is not None:
+                hit[0].replay()
+                self.launches += hit[1]
+            elif self._warm.get(key, 0) < 1:
+                core()                                   # first pass eager: kernel attributes get configured
+                self._warm[key] = 1
+            else:
+                n0 = self.launches
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    core()
+                if len(self._graphs) >= 8:
+                    self._graphs.clear()
+                self._graphs[key] = (g, self.launches - n0)
+                g.replay()
+        else:
+            core()
+        mode = 1 if (mod.track_map_resize == 'nearest' or pk.stride == 1) else 0
+        L('mask_upsample', ops.mask_upsample, LOW, out_mask, Bc, T, Ho, Wo, mod.output_channels, pk.pp, pk.stride,
+          mode, nbytes=4.0 * out_mask.numel())
+        if out_flags is not None:
+            L('flag_mean', ops.flag_mean, LOW, out_flags, Bc, N, T, mod.flag_channels, pk.flag_col0)
+
+    def _core(self, mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag):
+        X, A, QKV, O, OCLS, LOW = ws['X'], ws['A'], ws['QKV'], ws['O'], ws['OCLS'], ws['LOW']
+        H = ws['H'][:R * 4 * D].view(R, 4 * D)
+        PM = ws['H'][:M * Kp].view(M, Kp)
+        L, G = self._launch, self._gemm
         L('embed_init', ops.embed_init, X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D, nbytes=4.0 * R * D)
         G('gemm_patch', PM, pk.patch_w, None, X[:M], EPI_F32_ADD)
         Rs = R if use_cls else M
@@ -269,8 +309,3 @@ class SeekerEngine:
         else:
             L('ln', ops.layernorm, X[:M], None, None, A[:M], nbytes=ln_bytes(M))
         G('gemm_head', A[:M], pk.head_w, pk.head_b, LOW, EPI_F32_STORE)
-        mode = 1 if (mod.track_map_resize == 'nearest' or pk.stride == 1) else 0
-        L('mask_upsample', ops.mask_upsample, LOW, out_mask, Bc, T, Ho, Wo, mod.output_channels, pk.pp, pk.stride,
-          mode, nbytes=4.0 * out_mask.numel())
-        if out_flags is not None:
-            L('flag_mean', ops.flag_mean, LOW, out_flags, Bc, N, T, mod.flag_channels, pk.flag_col0)
