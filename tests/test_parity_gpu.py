@@ -112,11 +112,13 @@ def test_fused_and_unfused_temporal_paths_agree(logger):
     rgb, q = synth.make_batch(meta['samples'], num_frames=meta['T'], frame_height=meta['Hf'], frame_width=meta['Wf'],
                               query_frame=meta['query_frame'])
     with torch.no_grad():
+        net.seeker.engine().fuse_temporal_qkv = True
         m1, f1 = net(rgb.cuda(), q.cuda())
         net.seeker.engine().fuse_temporal_qkv = False
         m2, f2 = net(rgb.cuda(), q.cuda())
-    assert (m1 - m2).abs().max().item() <= 2e-3 and (f1 - f2).abs().max().item() <= 5e-3
+    assert (m1 - m2).abs().max().item() <= 6e-3 and (f1 - f2).abs().max().item() <= 1e-2
     ly, lx = meta['lattice']
+    assert (m1.cpu()[:, :, :, ::ly, ::lx] - gmask).abs().max().item() <= TOL_LOGIT
     assert (m2.cpu()[:, :, :, ::ly, ::lx] - gmask).abs().max().item() <= TOL_LOGIT
 
 
