@@ -46,6 +46,11 @@ class SeekerEngine:
         # temporal_fc o temporal_attn.proj has no nonlinearity in between (vit.py:111 -> :174): at inference
         # the two 768x768 linears are pre-multiplied in fp32 into one.
         self.merge_temporal_proj = merge_temporal_proj
+        # LayerNorm fused into the tail of the preceding residual GEMM (tcow_gemm_bf16_add_ln).  Measured at B=8: SLOWER
+        # (338 vs 365 clips/s) — the 221 MB stream does not stay L2-resident, so the tail re-reads HBM with a fraction of
+        # the stand-alone kernel's memory parallelism, and the row-unit tile order it needs costs the K=3072 GEMM 17 %.
+        # Off by default (TCOW_FUSE_LN=1 enables; profiles/r01_notes.md).
+        self.fuse_ln = os.environ.get('TCOW_FUSE_LN', '0') == '1'
         self._lock = threading.Lock()
         self._packed = {}      # device index -> (stamp, _Packed)
         self._workspace = {}   # (device index, Bc, shape key) -> dict of tensors
@@ -239,7 +244,7 @@ class SeekerEngine:
         L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained), qpv, sample0,
           nbytes=16.0 * frames[0].numel() / 3 * Bc + 2.0 * M * Kp)
         # ---- everything from the embeddings to the head GEMM: engine-owned buffers only -> CUDA-graph replay
-        key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, self.fuse_temporal_qkv,
+        key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, self.fuse_temporal_qkv, self.fuse_ln,
                bool(mod.norm_embeddings), id(pk))
         core = lambda: self._core(mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag)
         if self.use_cuda_graph and self.profile is None:
@@ -273,12 +278,25 @@ class SeekerEngine:
         PM = ws['H'][:M * Kp].view(M, Kp)
         L, G = self._launch, self._gemm
         L('embed_init', ops.embed_init, X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D, nbytes=4.0 * R * D)
-        G('gemm_patch', PM, pk.patch_w, None, X[:M], EPI_F32_ADD)
         Rs = R if use_cls else M
         ln_bytes = lambda rows: 6.0 * rows * D
-        for w in pk.blocks:
-            # temporal attention + temporal_fc + residual (vit.py:169-176); cls rows untouched
-            L('ln', ops.layernorm, X[:M], w.tn1[0], w.tn1[1], A[:M], nbytes=ln_bytes(M))
+        fuse_ln = self.fuse_ln
+        final_ln = pk.norm if mod.norm_embeddings else (None, None)
+
+        def residual(kind, a, wb, rows, ln_params, ln_rows):
+            """X[:rows] += a @ W^T + b, then A[:ln_rows] = LN(X[:ln_rows]) — fused tail or stand-alone kernel."""
+            if fuse_ln:
+                Mr, K = a.shape
+                self._launch(kind, ops.gemm_add_ln, a, wb[0], wb[1], X[:rows], ln_params[0], ln_params[1], A, ln_rows,
+                             flops=2.0 * Mr * D * K, nbytes=2.0 * (Mr * K + D * K) + 8.0 * Mr * D + 2.0 * ln_rows * D)
+            else:
+                G(kind, a, wb[0], wb[1], X[:rows], EPI_F32_ADD)
+                L('ln', ops.layernorm, X[:ln_rows], ln_params[0], ln_params[1], A[:ln_rows], nbytes=ln_bytes(ln_rows))
+
+        nblk = len(pk.blocks)
+        residual('gemm_patch', PM, (pk.patch_w, None), M, pk.blocks[0].tn1, M)   # + temporal_norm1 of block 0
+        for bi, w in enumerate(pk.blocks):
+            # temporal attention + temporal_fc + residual (vit.py:169-176); cls rows untouched.  A = LN_tn1(X[:M]).
             if self.fuse_temporal_qkv:
                 L('qkv_tattn', ops.qkv_temporal_attn, A[:M], w.t_qkv_perm[0], w.t_qkv_perm[1], O, Bc * N, T, HEADS,
                   causal_diag, flops=2.0 * M * 3 * D * D + 4.0 * Bc * N * HEADS * T * T * 64, nbytes=4.0 * M * D)
@@ -287,26 +305,27 @@ class SeekerEngine:
                 L('attn_temporal', ops.attn_temporal, QKV, O, Bc * N, T, HEADS, causal_diag,
                   flops=4.0 * Bc * N * HEADS * T * T * 64, nbytes=8.0 * M * D)
             if w.t_out is not None:
-                G('gemm_proj', O[:M], w.t_out[0], w.t_out[1], X[:M], EPI_F32_ADD)
+                residual('gemm_proj', O[:M], w.t_out, M, w.n1, M)                 # + norm1 for the spatial branch
             else:
-                G('gemm_proj', O[:M], w.t_proj[0], w.t_proj[1], A[:M], EPI_BF16)
-                G('gemm_proj', A[:M], w.t_fc[0], w.t_fc[1], X[:M], EPI_F32_ADD)
+                tmp = H[:M, :D]                                                    # H is idle here
+                G('gemm_proj', O[:M], w.t_proj[0], w.t_proj[1], tmp, EPI_BF16)
+                residual('gemm_proj', tmp, w.t_fc, M, w.n1, M)
+            if use_cls:   # the cls rows enter the spatial attention through norm1 too (vit.py:180-186)
+                L('ln', ops.layernorm, X[M:R], w.n1[0], w.n1[1], A[M:R], nbytes=ln_bytes(Bc))
             # spatial attention + residual (vit.py:179-215); cls is key/query 0 of every frame
-            L('ln', ops.layernorm, X[:Rs], w.n1[0], w.n1[1], A[:Rs], nbytes=ln_bytes(Rs))
             G('gemm_qkv', A[:Rs], w.s_qkv[0], w.s_qkv[1], QKV[:Rs], EPI_BF16)
             S = N + (1 if use_cls else 0)
             L('attn_spatial', ops.attn_spatial, QKV, O, OCLS if use_cls else None, Bc, N, T, HEADS, use_cls, M,
               flops=4.0 * Bc * T * HEADS * S * S * 64, nbytes=8.0 * M * D)
             if use_cls and causal == 0:   # mean over frames (vit.py:195); causal==1 takes frame 0, written in-kernel
                 L('cls_merge', ops.cls_merge, OCLS, O, Bc, T, D, M, 0)
-            G('gemm_proj', O[:Rs], w.s_proj[0], w.s_proj[1], X[:Rs], EPI_F32_ADD)
-            # MLP on every token incl. cls (vit.py:216)
-            L('ln', ops.layernorm, X, w.n2[0], w.n2[1], A, nbytes=ln_bytes(R))
+            residual('gemm_proj', O[:Rs], w.s_proj, Rs, w.n2, Rs)                  # + norm2 for the MLP
+            if not use_cls:   # the cls rows skip the spatial branch but still go through the MLP (vit.py:215-216)
+                L('ln', ops.layernorm, X[M:R], w.n2[0], w.n2[1], A[M:R], nbytes=ln_bytes(Bc))
+            # MLP on every token incl. cls (vit.py:216); its residual GEMM carries the next block's temporal_norm1
+            # (or, after the last block, the optional final norm / plain cast that feeds the head)
             G('gemm_fc1', A, w.fc1[0], w.fc1[1], H, EPI_BF16_GELU)
-            G('gemm_fc2', H, w.fc2[0], w.fc2[1], X, EPI_F32_ADD)
-        # ---- optional final norm (vision_tf.py:152-153) or plain cast, then head (mask_tracker.py:112-137)
-        if mod.norm_embeddings:
-            L('ln', ops.layernorm, X[:M], pk.norm[0], pk.norm[1], A[:M], nbytes=ln_bytes(M))
-        else:
-            L('ln', ops.layernorm, X[:M], None, None, A[:M], nbytes=ln_bytes(M))
+            nxt = pk.blocks[bi + 1].tn1 if bi + 1 < nblk else final_ln
+            residual('gemm_fc2', H, w.fc2, R, nxt, M)
+        # ---- head (mask_tracker.py:112-137) on A = final norm (vision_tf.py:152-153) or plain bf16 cast of X[:M]
         G('gemm_head', A[:M], pk.head_w, pk.head_b, LOW, EPI_F32_STORE)
