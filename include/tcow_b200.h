@@ -39,6 +39,8 @@ extern "C" {
 #define TCOW_EPI_F32_STORE 2 /* C(fp32)  = A W^T + bias                       (head: mask_tracker.py:113) */
 #define TCOW_EPI_F32_ADD 3   /* C(fp32) += A W^T + bias   (proj/temporal_fc/fc2 + residual: vit.py:176,215-216) */
 #define TCOW_EPI_F32_ADD_LN 4 /* internal: F32_ADD followed by the LayerNorm tail of tcow_gemm_bf16_add_ln */
+#define TCOW_EPI_BF16_GELU_AUX 5 /* training fc1: aux(bf16) = z = A W^T + bias and C(bf16) = gelu_erf(z) (vit.py:55-56) */
+#define TCOW_EPI_BF16_DGELU 6    /* backward of the above: C(bf16) = (A W^T) * gelu_erf'(aux)                      */
 
 /* Library / device checks. */
 int tcow_abi_version(void);
@@ -120,6 +122,76 @@ int tcow_mask_upsample(const float* low, int64_t ld_low, float* out, int B, int 
 /* Flags (mask_tracker.py:135-137): flags[b,t,f] = mean_n low[(b*N+n)*T+t, col0+f]. */
 int tcow_flag_mean(const float* low, int64_t ld_low, float* flags, int B, int N, int T, int F, int col0,
                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step (BASELINE configs[3]: fwd+bwd, data-parallel).  The reference gets its backward from torch.autograd
+ * over the modules cited above (train.py:93-101 loss.backward(); optimizer.step()); these entry points are the
+ * hand-written adjoints, driven by tcow_b200/train_engine.py behind a torch.autograd.Function.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* GEMM with an auxiliary bf16 tensor aux[M,N] (pitch ldaux):
+ *  TCOW_EPI_BF16_GELU_AUX: aux = z = A W^T + bias, C = gelu_erf(z)        (Mlp.fc1 + act saving the pre-activation)
+ *  TCOW_EPI_BF16_DGELU:    C = (A W^T) * gelu_erf'(aux)                    (dZ = (dY W2) o gelu'(z), bias must be NULL) */
+int tcow_gemm_bf16_aux(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                       void* aux, int64_t ldaux, int M, int N, int K, int epilogue, void* stream);
+
+/* Weight gradient of nn.Linear:  dW[N1,N2] (fp32) += A[R,N1]^T (bf16) x B[R,N2] (bf16), contraction over the R
+ * token rows (A = dY, B = the layer input).  tcgen05 with both operands MN-major (no transposes in memory), split
+ * along R, partial products combined with TMA reduce-add: the caller zeroes dW (or accumulates across micro-batches).
+ * N1, N2 multiples of 64. */
+int tcow_gemm_bf16_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, int R, int N1,
+                         int N2, void* stream);
+
+/* Floats of scratch the reductions below need (LayerNorm-backward / column-sum / time-embedding partial sums). */
+int64_t tcow_train_workspace_floats(int max_cols);
+
+/* LayerNorm forward that also saves what the backward needs: y = xhat*gamma+beta (bf16), xhat (bf16), rstd (fp32). */
+int tcow_layernorm_bf16_train(const float* x, const float* gamma, const float* beta, void* y, void* xhat, float* rstd,
+                              int rows, int D, float eps, void* stream);
+
+/* LayerNorm backward fused with the residual-gradient update: with g = dy*gamma,
+ *   dx = rstd * (g - mean(g) - xhat*mean(g*xhat));  G[rows,D] (fp32) = (accumulate ? G : 0) + dx;  Gb = bf16(G);
+ *   dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy   (deterministic two-stage reduction through `workspace`). */
+int tcow_layernorm_bwd(const void* dy, const void* xhat, const float* rstd, const float* gamma, float* G, void* Gb,
+                       float* dgamma, float* dbeta, float* workspace, int rows, int D, int accumulate, void* stream);
+
+/* Bias gradient: out[N] (fp32) = (accumulate ? out : 0) + sum_r x[r, :] for x bf16 [rows, N] (pitch ldx). */
+int tcow_colsum_bf16(const void* x, int64_t ldx, int rows, int N, float* out, float* workspace, int accumulate,
+                     void* stream);
+
+/* Embedding gradients (adjoint of tcow_embed_init, vision_tf.py:99-138) from the residual-stream gradient G[M+B, D]:
+ *   dpos[1+n] (+)= sum_{b,t} G[(b*N+n)*T+t];  dtime[t] (+)= sum_{b,n} G[(b*N+n)*T+t];  dcls_pos0 (+)= sum_b G[M+b]
+ * (dcls_pos0 is the gradient of both cls_token and pos_embed[0]; the conv bias gradient is sum_t dtime[t]). */
+int tcow_embed_bwd(const float* G, float* dpos, float* dtime, float* dcls_pos0, float* workspace, int B, int N, int T,
+                   int D, int accumulate, void* stream);
+
+/* Adjoint of tcow_mask_upsample + tcow_flag_mean: d_out [B,C,T,Hf,Wf] fp32 and d_flags [B,T,F] fp32 (or NULL) ->
+ * d_low [M, ld_low] bf16: columns [0,col0) the pooled-patch gradients, [col0,col0+F) d_flags/N, rest zero up to
+ * ncols (the dY operand of the head's weight-gradient and input-gradient GEMMs). */
+int tcow_mask_head_bwd(const float* d_out, const float* d_flags, void* d_low, int64_t ld_low, int B, int T, int Ho,
+                       int Wo, int C, int pp, int stride, int mode, int F, int col0, int ncols, void* stream);
+
+/* Spatial attention forward that also writes the base-2 log-sum-exp of every query token: lse [B*T*heads, 304]. */
+int tcow_attn_spatial_train(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, float* lse,
+                            int B, int N, int T, int heads, int use_cls, int64_t cls_row0, void* stream);
+
+/* Backward of tcow_attn_temporal: d_qkv[rows, 3*heads*64] (bf16) from qkv, the saved output `out` and d_out. */
+int tcow_attn_temporal_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* d_out,
+                           int64_t ld_do, void* d_qkv, int64_t ld_dqkv, int num_seq, int T, int heads, int causal_diag,
+                           void* stream);
+
+/* Backward of tcow_attn_spatial(_train).  out / d_out: patch rows (bf16); out_cls / d_out_cls: the cls query's
+ * per-frame output and its gradient, [B,T,heads*64] fp32; lse from the forward; d_cls: scratch [B,T,3,heads*64]
+ * fp32.  Writes d_qkv for every patch row and (summed over the frames) for row cls_row0+b. */
+int tcow_attn_spatial_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* out_cls,
+                          const void* d_out, int64_t ld_do, const float* d_out_cls, const float* lse, void* d_qkv,
+                          int64_t ld_dqkv, float* d_cls, int B, int N, int T, int heads, int use_cls, int64_t cls_row0,
+                          void* stream);
+
+/* Adjoint of the cls read-out (tcow_cls_merge / the in-kernel frame-0 write): d_out_cls[b,t,:] (fp32) =
+ * d_out[cls_row0+b,:] * (mode 0: 1/T for all t; mode 1: 1 for t == 0, else 0). */
+int tcow_cls_merge_bwd(const void* d_out, int64_t ld_out, float* d_out_cls, int B, int T, int D, int64_t cls_row0,
+                       int mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get('TCOW_B200_LIB') or os.path.join(_HERE, 'libtcow_b200.
 
 TCOW_ERR_ARG, TCOW_ERR_CUDA, TCOW_ERR_ARCH = -1, -2, -3
 EPI_BF16, EPI_BF16_GELU, EPI_F32_STORE, EPI_F32_ADD = 0, 1, 2, 3
+EPI_BF16_GELU_AUX, EPI_BF16_DGELU = 5, 6
 
 # name -> argtypes (restype is int unless noted); mirrors include/tcow_b200.h one to one.
 SIGNATURES = {
@@ -35,6 +36,26 @@ SIGNATURES = {
     'tcow_mask_upsample': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                            c_void_p],
     'tcow_flag_mean': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    # ---- training step
+    'tcow_gemm_bf16_aux': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                           c_int, c_int, c_int, c_int, c_void_p],
+    'tcow_gemm_bf16_wgrad': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
+    'tcow_train_workspace_floats': [c_int],
+    'tcow_layernorm_bf16_train': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                  c_void_p],
+    'tcow_layernorm_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_int, c_int, c_int, c_void_p],
+    'tcow_colsum_bf16': [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    'tcow_embed_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'tcow_mask_head_bwd': [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_int, c_int, c_int, c_int, c_void_p],
+    'tcow_attn_spatial_train': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_int, c_int64, c_void_p],
+    'tcow_attn_temporal_bwd': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int,
+                               c_int, c_int, c_int, c_void_p],
+    'tcow_attn_spatial_bwd': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                              c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p],
+    'tcow_cls_merge_bwd': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_void_p],
 }
 
 _lib = None
@@ -55,7 +76,8 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
-            fn.restype = c_char_p if name == 'tcow_last_error' else c_int
+            fn.restype = (c_char_p if name == 'tcow_last_error' else
+                          c_int64 if name == 'tcow_train_workspace_floats' else c_int)
         _lib = lib
     return _lib
 

@@ -363,6 +363,19 @@ extern "C" int tcow_attn_spatial(const void* qkv, int64_t ld_qkv, void* out, int
   return launch_spatial<4>(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
 }
 
+extern "C" int tcow_attn_spatial_train(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls,
+                                       float* lse, int B, int N, int T, int heads, int use_cls, int64_t cls_row0,
+                                       void* stream) {
+  using namespace tcow;
+  if (!qkv || !out || !lse || B <= 0 || N <= 0 || T <= 0 || heads <= 0) return set_error(TCOW_ERR_ARG, "attn_spatial_train: bad argument");
+  if (use_cls && !out_cls) return set_error(TCOW_ERR_ARG, "attn_spatial_train: out_cls required when use_cls");
+  if ((ld_qkv % 8) || (ld_out % 8)) return set_error(TCOW_ERR_ARG, "attn_spatial_train: row pitches must be multiples of 8");
+  if (N + (use_cls ? 1 : 0) > 304)
+    return set_error(TCOW_ERR_ARG, "attn_spatial_train: %d tokens per frame > 304 not supported in training", N + (use_cls ? 1 : 0));
+  return launch_spatial_tc(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0,
+                           static_cast<cudaStream_t>(stream), lse);
+}
+
 extern "C" int tcow_cls_merge(const float* out_cls, void* out, int64_t ld_out, int B, int T, int D, int64_t cls_row0,
                               int mode, void* stream) {
   using namespace tcow;

@@ -41,6 +41,7 @@ struct SpatialArgs {
   int B, N, T, heads, use_cls;
   int64_t cls_row0;
   float scale_log2;
+  float* lse;       // training: [B*T*heads][304] base-2 log-sum-exp of the scaled scores per query token (or nullptr)
   long long* prof;  // SP_PROFILE builds only
 };
 
@@ -410,6 +411,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
         tmem_ld_wait();
         if (valid) {
           const float inv = 1.0f / l_run;
+          if (a.lse) a.lse[static_cast<int64_t>(item) * SP_ROWS + tok] = fmaf(m_run, sc, log2f(l_run));
           if (a.use_cls && tok == N) {
             float4* dst = reinterpret_cast<float4*>(a.out_cls + (static_cast<int64_t>(b) * T + t) * D + h * 64);
 #pragma unroll
@@ -483,7 +485,7 @@ static int make_patch_tmap(CUtensorMap* m, const void* qkv, int64_t ld, int cols
 }
 
 int launch_spatial_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N, int T,
-                      int heads, int use_cls, int64_t cls_row0, cudaStream_t stream) {
+                      int heads, int use_cls, int64_t cls_row0, cudaStream_t stream, float* lse) {
   alignas(64) CUtensorMap tmQf, tmQt, tmKVf, tmKVt;
   const int cols = 3 * heads * 64;
   const int q_tail = N % 128, kv_full = N < 256 ? N : 256, kv_tail = N - kv_full;
@@ -501,7 +503,7 @@ int launch_spatial_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out
     configured[dev & 63] = true;
   }
   SpatialArgs a{static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<__nv_bfloat16*>(out), ld_out, out_cls,
-                B, N, T, heads, use_cls, cls_row0, 0.125f * 1.4426950408889634f, nullptr};
+                B, N, T, heads, use_cls, cls_row0, 0.125f * 1.4426950408889634f, lse, nullptr};
 #ifdef SP_PROFILE
   static long long* dprof = nullptr;
   if (!dprof) cudaMalloc(&dprof, 16 * 8 * 512);

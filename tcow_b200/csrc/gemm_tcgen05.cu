@@ -30,8 +30,13 @@ struct GemmCfg {
   static constexpr bool LN_TAIL = (EPI == TCOW_EPI_F32_ADD_LN);
   static constexpr bool RED_ADD = (EPI == TCOW_EPI_F32_ADD || LN_TAIL);
   static constexpr bool OUT_F32 = (EPI == TCOW_EPI_F32_STORE || RED_ADD);
+  // training epilogues: GELU_AUX also stores the pre-activation (second TMA store through tmAux); DGELU multiplies
+  // the accumulator by gelu'(z), z read from the saved pre-activation
+  static constexpr bool GELU_AUX = (EPI == TCOW_EPI_BF16_GELU_AUX);
+  static constexpr bool DGELU = (EPI == TCOW_EPI_BF16_DGELU);
+  static constexpr bool GELU_LIKE = (EPI == TCOW_EPI_BF16_GELU || GELU_AUX || DGELU);
   // The GELU epilogue is issue-bound (exact-erf on 128x256 values per tile): give it 8 warps, 4 otherwise.
-  static constexpr int EPI_WARPS = (EPI == TCOW_EPI_BF16_GELU && BN >= 128) ? 8 : 4;
+  static constexpr int EPI_WARPS = (GELU_LIKE && BN >= 128) ? 8 : 4;
   // LN-tail mode: 4 more warps do nothing but the LayerNorm read-back, so that its (latency-bound) L2/HBM round trips
   // overlap the epilogue instead of extending it.
   static constexpr int LN_WARPS = (EPI == TCOW_EPI_F32_ADD_LN) ? 4 : 0;
@@ -92,6 +97,29 @@ __device__ __forceinline__ uint64_t gelu_erf2(float x0, float x1) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-ww1));
   const uint64_t h = f2_mul(q, f2_pack(e0, e1));
   return f2_fma(na, h, f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+
+// d/dx gelu_erf(x) = Phi(x) + x*phi(x) with the same erfcx polynomial: h = q(|x|) e, e = exp(-x^2/2);
+// Phi = 1-h (x >= 0) or h (x < 0); phi = e / sqrt(2 pi).  Backward of nn.GELU() (vit.py:46,56).
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float na = fmaxf(-fabsf(x), -5.75f);
+  float q = 1.740049385e-07f;
+  q = fmaf(q, na, 5.850045000e-06f);
+  q = fmaf(q, na, 8.705152140e-05f);
+  q = fmaf(q, na, 7.601087564e-04f);
+  q = fmaf(q, na, 4.371289164e-03f);
+  q = fmaf(q, na, 1.773692295e-02f);
+  q = fmaf(q, na, 5.366283283e-02f);
+  q = fmaf(q, na, 1.275363415e-01f);
+  q = fmaf(q, na, 2.482131273e-01f);
+  q = fmaf(q, na, 3.987075090e-01f);
+  q = fmaf(q, na, 4.999948144e-01f);
+  const float w = na * 0.84932180028801904f;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-w * w));
+  const float h = q * e;
+  const float Phi = x >= 0.f ? 1.f - h : h;
+  return fmaf(x * 0.3989422804014327f, e, Phi);
 }
 
 // LayerNorm tail of the residual epilogue (EPI_F32_ADD_LN): once a warp's TMA reduce-adds for ALL column tiles of its
@@ -168,7 +196,8 @@ template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GemmCfg<BN, EPI, CL>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
-                    const LnTail ln) {
+                    const LnTail ln, const __grid_constant__ CUtensorMap tmAux, const __nv_bfloat16* __restrict__ aux,
+                    int64_t ldaux) {
   using Cfg = GemmCfg<BN, EPI, CL>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool PAIR = Cfg::PAIR;
@@ -382,29 +411,56 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (PAIR) mbar_arrive_cluster(tempty_bar(acc), 0);  // the pair's MMA issuer lives in the leader CTA
             else mbar_arrive(tempty_bar(acc));
           }
+          const int grow = m_blk * BM + ew * 32 + lane;  // this thread's output row
+          const uint4* zrow = nullptr;
+          if constexpr (Cfg::DGELU) zrow = reinterpret_cast<const uint4*>(aux + static_cast<int64_t>(grow) * ldaux + col0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t* v = (j < 4) ? (v0 + 8 * j) : (v1 + 8 * (j - 4));
-            float4 b0 = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + 2 * j) : make_float4(0, 0, 0, 0);
-            float4 b1 =
-                bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + 2 * j + 1) : make_float4(0, 0, 0, 0);
-            float f[8];
-            f[0] = __uint_as_float(v[0]) + b0.x;
-            f[1] = __uint_as_float(v[1]) + b0.y;
-            f[2] = __uint_as_float(v[2]) + b0.z;
-            f[3] = __uint_as_float(v[3]) + b0.w;
-            f[4] = __uint_as_float(v[4]) + b1.x;
-            f[5] = __uint_as_float(v[5]) + b1.y;
-            f[6] = __uint_as_float(v[6]) + b1.z;
-            f[7] = __uint_as_float(v[7]) + b1.w;
-            if constexpr (EPI == TCOW_EPI_BF16_GELU) {
-#pragma unroll
-              for (int e = 0; e < 8; e += 2) f2_unpack(gelu_erf2(f[e], f[e + 1]), f[e], f[e + 1]);
+          for (int pass = 0; pass < (Cfg::GELU_AUX ? 2 : 1); ++pass) {
+            if (pass == 1) {  // the pre-activation store must have drained the staging buffer before gelu(z) reuses it
+              if (elect_one()) tma_wait_group_read<0>();
+              __syncwarp();
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + srow + ((j ^ sw) << 4)),
-                         "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])),
-                         "r"(pack_bf16(f[6], f[7]))
-                         : "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t* v = (j < 4) ? (v0 + 8 * j) : (v1 + 8 * (j - 4));
+              float4 b0 = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + 2 * j) : make_float4(0, 0, 0, 0);
+              float4 b1 =
+                  bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + 2 * j + 1) : make_float4(0, 0, 0, 0);
+              float f[8];
+              f[0] = __uint_as_float(v[0]) + b0.x;
+              f[1] = __uint_as_float(v[1]) + b0.y;
+              f[2] = __uint_as_float(v[2]) + b0.z;
+              f[3] = __uint_as_float(v[3]) + b0.w;
+              f[4] = __uint_as_float(v[4]) + b1.x;
+              f[5] = __uint_as_float(v[5]) + b1.y;
+              f[6] = __uint_as_float(v[6]) + b1.z;
+              f[7] = __uint_as_float(v[7]) + b1.w;
+              if (EPI == TCOW_EPI_BF16_GELU || (Cfg::GELU_AUX && pass == 1)) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) f2_unpack(gelu_erf2(f[e], f[e + 1]), f[e], f[e + 1]);
+              }
+              if constexpr (Cfg::DGELU) {
+                const uint4 zz = grow < M ? __ldg(zrow + j) : make_uint4(0, 0, 0, 0);
+                const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f[2 * e] *= dgelu_erf(__uint_as_float(zw[e] << 16));
+                  f[2 * e + 1] *= dgelu_erf(__uint_as_float(zw[e] & 0xffff0000u));
+                }
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + srow + ((j ^ sw) << 4)),
+                           "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])),
+                           "r"(pack_bf16(f[6], f[7]))
+                           : "memory");
+            }
+            if (Cfg::GELU_AUX && pass == 0) {  // z = A W^T + b goes out through the second tensor map
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (elect_one()) {
+                tma_store_2d(&tmAux, buf, col0, m_blk * BM + ew * 32);
+                tma_commit_group();
+              }
+            }
           }
         }
         fence_proxy_async_smem();
@@ -475,7 +531,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------ host side
 template <int BN, int EPI, int CL>
 static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
-                       int64_t ldc, int M, int N, int K, cudaStream_t stream, const LnTail& ln = LnTail{}) {
+                       int64_t ldc, int M, int N, int K, cudaStream_t stream, const LnTail& ln = LnTail{},
+                       const void* aux = nullptr, int64_t ldaux = 0) {
   using Cfg = GemmCfg<BN, EPI, CL>;
   constexpr int CS = Cfg::CSIZE;
   alignas(64) CUtensorMap tmA, tmB, tmC;
@@ -483,6 +540,8 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
   if ((rc = make_tmap_2d(&tmA, false, A, K, M, lda, BK, BM))) return rc;
   if ((rc = make_tmap_2d(&tmB, false, W, K, N, ldw, BK, BN / CS))) return rc;
   if ((rc = make_tmap_2d(&tmC, Cfg::OUT_F32, C, N, M, ldc, Cfg::CHUNK_COLS, 32))) return rc;
+  alignas(64) CUtensorMap tmAux = tmC;
+  if (Cfg::GELU_AUX && (rc = make_tmap_2d(&tmAux, false, aux, N, M, ldaux, Cfg::CHUNK_COLS, 32))) return rc;
   auto kern = gemm_bf16_tn_kernel<BN, EPI, CL>;
   static bool configured[64] = {};
   int dev = 0;
@@ -508,7 +567,8 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, bias, M, N, K, ln);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, bias, M, N, K, ln, tmAux,
+                                     static_cast<const __nv_bfloat16*>(aux), ldaux);
   if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "gemm_bf16_tn_kernel: launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_tn_kernel");
 }
@@ -521,21 +581,23 @@ static int cluster_mode(int M, int epi) {
   if (forced >= 1 && forced <= 3) return forced;
   // The GELU epilogue is the longest; coupling two CTAs' epilogues to one accumulator hand-off (pair mode) costs
   // it ~4 % (measured), so it keeps independent CTAs sharing the weight tile by multicast.
-  return epi == TCOW_EPI_BF16_GELU ? 2 : 3;
+  return (epi == TCOW_EPI_BF16_GELU || epi == TCOW_EPI_BF16_GELU_AUX || epi == TCOW_EPI_BF16_DGELU) ? 2 : 3;
 }
 
 template <int EPI>
 static int dispatch_bn(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
-                       int64_t ldc, int M, int N, int K, cudaStream_t stream) {
+                       int64_t ldc, int M, int N, int K, cudaStream_t stream, const void* aux = nullptr,
+                       int64_t ldaux = 0) {
+  const LnTail none{};
   if (N % 256 == 0) {
     switch (cluster_mode(M, EPI)) {
-      case 3: return launch_gemm<256, EPI, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-      case 2: return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-      default: return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+      case 3: return launch_gemm<256, EPI, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
+      case 2: return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
+      default: return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
     }
   }
-  if (N % 128 == 0) return launch_gemm<128, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
-  return launch_gemm<64, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream);
+  if (N % 128 == 0) return launch_gemm<128, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
+  return launch_gemm<64, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
 }
 
 }  // namespace tcow
@@ -556,6 +618,27 @@ extern "C" int tcow_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
     case TCOW_EPI_F32_ADD: return dispatch_bn<TCOW_EPI_F32_ADD>(A, lda, W, ldw, bias, C, ldc, M, N, K, s);
   }
   return set_error(TCOW_ERR_ARG, "gemm: unknown epilogue %d", epilogue);
+}
+
+extern "C" int tcow_gemm_bf16_aux(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+                                  int64_t ldc, void* aux, int64_t ldaux, int M, int N, int K, int epilogue,
+                                  void* stream) {
+  using namespace tcow;
+  if (!A || !W || !C || !aux) return set_error(TCOW_ERR_ARG, "gemm_aux: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(TCOW_ERR_ARG, "gemm_aux: non-positive dimension");
+  if (N % 64 != 0 || K % 64 != 0)
+    return set_error(TCOW_ERR_ARG, "gemm_aux: N (%d) and K (%d) must be multiples of 64", N, K);
+  if ((ldaux % 8) || (reinterpret_cast<uintptr_t>(aux) & 15))
+    return set_error(TCOW_ERR_ARG, "gemm_aux: aux must be 16-byte aligned with a 16-byte-multiple pitch");
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return set_error(TCOW_ERR_ARG, "gemm_aux: bias must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (epilogue) {
+    case TCOW_EPI_BF16_GELU_AUX:
+      return dispatch_bn<TCOW_EPI_BF16_GELU_AUX>(A, lda, W, ldw, bias, C, ldc, M, N, K, s, aux, ldaux);
+    case TCOW_EPI_BF16_DGELU:
+      return dispatch_bn<TCOW_EPI_BF16_DGELU>(A, lda, W, ldw, bias, C, ldc, M, N, K, s, aux, ldaux);
+  }
+  return set_error(TCOW_ERR_ARG, "gemm_aux: epilogue %d takes no auxiliary tensor", epilogue);
 }
 
 extern "C" int tcow_gemm_bf16_add_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* X,

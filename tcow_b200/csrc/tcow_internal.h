@@ -15,5 +15,5 @@ int make_tmap_2d(void* map, bool is_f32, const void* ptr, uint64_t inner, uint64
                  uint32_t box_inner, uint32_t box_rows);
 // tcgen05/TMEM spatial attention (attn_spatial_tc.cu); valid for N + use_cls <= 304.
 int launch_spatial_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N, int T,
-                      int heads, int use_cls, int64_t cls_row0, cudaStream_t stream);
+                      int heads, int use_cls, int64_t cls_row0, cudaStream_t stream, float* lse = nullptr);
 }  // namespace tcow

@@ -4,7 +4,8 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import EPI_BF16, EPI_BF16_GELU, EPI_F32_ADD, EPI_F32_STORE  # noqa: F401
+from ._lib import (EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_BF16_GELU_AUX, EPI_F32_ADD,  # noqa: F401
+                   EPI_F32_STORE)
 
 
 def _stream():
@@ -125,3 +126,114 @@ def mask_upsample(low, out, B, T, Ho, Wo, C, pp, stride, mode):
 def flag_mean(low, flags, B, N, T, F, col0):
     _lib.call('tcow_flag_mean', low.data_ptr(), low.stride(0), flags.data_ptr(), B, N, T, F, col0, _stream())
     return flags
+
+
+# ------------------------------------------------------------------------------------------------ training step
+def gemm_aux(a, w, bias, out, aux, epilogue):
+    """EPI_BF16_GELU_AUX: aux = a @ w^T + bias, out = gelu(aux);  EPI_BF16_DGELU: out = (a @ w^T) * gelu'(aux)."""
+    _chk(a, torch.bfloat16, 'gemm_aux.a'); _chk(w, torch.bfloat16, 'gemm_aux.w')
+    _chk(out, torch.bfloat16, 'gemm_aux.out'); _chk(aux, torch.bfloat16, 'gemm_aux.aux')
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or tuple(out.shape) != (M, N) or tuple(aux.shape) != (M, N):
+        raise ValueError('gemm_aux: shape mismatch')
+    _lib.call('tcow_gemm_bf16_aux', a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _p(bias), out.data_ptr(),
+              out.stride(0), aux.data_ptr(), aux.stride(0), M, N, K, epilogue, _stream())
+    return out
+
+
+def gemm_wgrad(dy, x, dw):
+    """dw[N1,N2] (fp32) += dy[R,N1]^T @ x[R,N2]  (bf16 operands, contraction over the token rows)."""
+    _chk(dy, torch.bfloat16, 'gemm_wgrad.dy'); _chk(x, torch.bfloat16, 'gemm_wgrad.x'); _chk(dw, torch.float32, 'gemm_wgrad.dw')
+    R, N1 = dy.shape
+    N2 = x.shape[1]
+    if x.shape[0] != R or tuple(dw.shape) != (N1, N2):
+        raise ValueError(f'gemm_wgrad: shape mismatch dy{tuple(dy.shape)} x{tuple(x.shape)} dw{tuple(dw.shape)}')
+    _lib.call('tcow_gemm_bf16_wgrad', dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
+              dw.stride(0), R, N1, N2, _stream())
+    return dw
+
+
+def train_workspace_floats(max_cols=4096):
+    return int(_lib.load().tcow_train_workspace_floats(int(max_cols)))
+
+
+def layernorm_train(x, gamma, beta, out, xhat, rstd, eps=1e-6):
+    _chk(x, torch.float32, 'layernorm_train.x'); _chk(out, torch.bfloat16, 'layernorm_train.out')
+    _chk(xhat, torch.bfloat16, 'layernorm_train.xhat'); _chk(rstd, torch.float32, 'layernorm_train.rstd')
+    rows, D = x.shape
+    if not (x.is_contiguous() and out.is_contiguous() and xhat.is_contiguous() and out.shape == x.shape
+            and xhat.shape == x.shape and rstd.numel() >= rows):
+        raise ValueError('layernorm_train: contiguous tensors of equal shape required')
+    _lib.call('tcow_layernorm_bf16_train', x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+              xhat.data_ptr(), rstd.data_ptr(), rows, D, float(eps), _stream())
+    return out
+
+
+def layernorm_bwd(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, accumulate=True):
+    _chk(dy, torch.bfloat16, 'layernorm_bwd.dy'); _chk(xhat, torch.bfloat16, 'layernorm_bwd.xhat')
+    _chk(G, torch.float32, 'layernorm_bwd.G'); _chk(Gb, torch.bfloat16, 'layernorm_bwd.Gb')
+    rows, D = dy.shape
+    for t in (dy, xhat, G, Gb):
+        if not t.is_contiguous() or tuple(t.shape) != (rows, D):
+            raise ValueError('layernorm_bwd: contiguous [rows, D] tensors required')
+    _lib.call('tcow_layernorm_bwd', dy.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), G.data_ptr(),
+              Gb.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), workspace.data_ptr(), rows, D, int(accumulate),
+              _stream())
+
+
+def colsum(x, out, workspace, accumulate=True):
+    _chk(x, torch.bfloat16, 'colsum.x'); _chk(out, torch.float32, 'colsum.out')
+    rows, N = x.shape
+    if out.numel() != N or workspace.numel() < 64 * N:
+        raise ValueError('colsum: output / workspace size mismatch')
+    _lib.call('tcow_colsum_bf16', x.data_ptr(), x.stride(0), rows, N, out.data_ptr(), workspace.data_ptr(),
+              int(accumulate), _stream())
+    return out
+
+
+def embed_bwd(G, dpos, dtime, dcls_pos0, workspace, B, N, T, D, accumulate=True):
+    _chk(G, torch.float32, 'embed_bwd.G')
+    _lib.call('tcow_embed_bwd', G.data_ptr(), dpos.data_ptr(), dtime.data_ptr(), _p(dcls_pos0), workspace.data_ptr(),
+              B, N, T, D, int(accumulate), _stream())
+
+
+def mask_head_bwd(d_out, d_flags, d_low, B, T, Ho, Wo, C, pp, stride, mode, F, col0):
+    _chk(d_out, torch.float32, 'mask_head_bwd.d_out'); _chk(d_low, torch.bfloat16, 'mask_head_bwd.d_low')
+    if not d_out.is_contiguous() or (d_flags is not None and not d_flags.is_contiguous()):
+        raise ValueError('mask_head_bwd: contiguous gradients required')
+    _lib.call('tcow_mask_head_bwd', d_out.data_ptr(), _p(d_flags), d_low.data_ptr(), d_low.stride(0), B, T, Ho, Wo, C,
+              pp, stride, mode, F, col0, d_low.shape[1], _stream())
+    return d_low
+
+
+def attn_spatial_train(qkv, out, out_cls, lse, B, N, T, heads, use_cls, cls_row0):
+    _chk(qkv, torch.bfloat16, 'attn_spatial_train.qkv'); _chk(out, torch.bfloat16, 'attn_spatial_train.out')
+    _chk(lse, torch.float32, 'attn_spatial_train.lse')
+    if lse.numel() < B * T * heads * 304:
+        raise ValueError('attn_spatial_train: lse must hold B*T*heads*304 floats')
+    _lib.call('tcow_attn_spatial_train', qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), _p(out_cls),
+              lse.data_ptr(), B, N, T, heads, int(use_cls), cls_row0, _stream())
+    return out
+
+
+def attn_temporal_bwd(qkv, out, d_out, d_qkv, num_seq, T, heads, causal_diag):
+    for t, n in ((qkv, 'qkv'), (out, 'out'), (d_out, 'd_out'), (d_qkv, 'd_qkv')):
+        _chk(t, torch.bfloat16, 'attn_temporal_bwd.' + n)
+    _lib.call('tcow_attn_temporal_bwd', qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), d_out.data_ptr(),
+              d_out.stride(0), d_qkv.data_ptr(), d_qkv.stride(0), num_seq, T, heads, causal_diag, _stream())
+    return d_qkv
+
+
+def attn_spatial_bwd(qkv, out, out_cls, d_out, d_out_cls, lse, d_qkv, d_cls, B, N, T, heads, use_cls, cls_row0):
+    for t, n in ((qkv, 'qkv'), (out, 'out'), (d_out, 'd_out'), (d_qkv, 'd_qkv')):
+        _chk(t, torch.bfloat16, 'attn_spatial_bwd.' + n)
+    _lib.call('tcow_attn_spatial_bwd', qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), _p(out_cls),
+              d_out.data_ptr(), d_out.stride(0), _p(d_out_cls), lse.data_ptr(), d_qkv.data_ptr(), d_qkv.stride(0),
+              _p(d_cls), B, N, T, heads, int(use_cls), cls_row0, _stream())
+    return d_qkv
+
+
+def cls_merge_bwd(d_out, d_out_cls, B, T, D, cls_row0, mode):
+    _lib.call('tcow_cls_merge_bwd', d_out.data_ptr(), d_out.stride(0), d_out_cls.data_ptr(), B, T, D, cls_row0, mode,
+              _stream())
