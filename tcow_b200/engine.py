@@ -186,8 +186,8 @@ class SeekerEngine:
             raise RuntimeError('tcow_b200 runs on a CUDA sm_100 device only; move the module and inputs to '
                                'the GPU (there is no CPU fallback)')
         if torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters()):
-            raise NotImplementedError('tcow_b200 round 1 implements the forward only; call under '
-                                      'torch.no_grad() (as pipeline.py set_phase("test") does)')
+            raise RuntimeError('SeekerEngine is the inference plan; gradient mode goes through '
+                               'tcow_b200.train_engine (QueryMaskTracker.forward dispatches on torch.is_grad_enabled())')
         device = input_frames.device
         bbm = mod.tracker_backbone
         V, Cin, T, Hf, Wf = input_frames.shape

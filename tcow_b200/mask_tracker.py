@@ -6,6 +6,7 @@ import torch
 
 from . import vision_tf
 from .engine import SeekerEngine
+from .train_engine import SeekerFunction, SeekerTrainEngine
 
 
 class QueryMaskTracker(torch.nn.Module):
@@ -68,11 +69,29 @@ class QueryMaskTracker(torch.nn.Module):
         assert self.frame_height % self.patch_size == 0
         assert self.frame_width % self.patch_size == 0
         self._engine = None  # built lazily on the parameters' device; not part of the state dict
+        self._train_engine = None
 
     def engine(self):
         if self._engine is None:
             self._engine = SeekerEngine(self)
         return self._engine
+
+    def train_engine(self):
+        if self._train_engine is None:
+            self._train_engine = SeekerTrainEngine(self)
+        return self._train_engine
+
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _forward_train(self, input_frames, query_mask, queries_per_video):
+        # autograd node over the hand-written backward (train_engine.py); gradients flow to the parameters only —
+        # the reference never differentiates w.r.t. its inputs either (train.py:93-101)
+        names = [n for n, _ in self.named_parameters()]
+        params = [p for _, p in self.named_parameters()]
+        (mask, flags) = SeekerFunction.apply(self.train_engine(), self, names, queries_per_video, input_frames,
+                                             query_mask, *params)
+        return (mask, flags if self.flag_channels > 0 else None)
 
     def forward(self, input_frames, query_mask):
         '''
@@ -81,6 +100,8 @@ class QueryMaskTracker(torch.nn.Module):
         :return (output_mask (B, C, T, Hf, Wf) fp32 logits, output_flags (B, T, F) fp32 or None).
         '''
         assert query_mask.shape[1] == 1                         # mask_tracker.py:105
+        if self._wants_grad():
+            return self._forward_train(input_frames, query_mask, 1)
         return self.engine().forward(self, input_frames, query_mask)
 
     def forward_queries(self, input_frames, query_masks):
@@ -94,8 +115,11 @@ class QueryMaskTracker(torch.nn.Module):
         assert query_masks.dim() == 6 and query_masks.shape[2] == 1
         (B, Qs) = query_masks.shape[:2]
         assert input_frames.shape[0] == B
-        (mask, flags) = self.engine().forward(self, input_frames, query_masks.reshape(B * Qs, *query_masks.shape[2:]),
-                                              queries_per_video=Qs)
+        flat_q = query_masks.reshape(B * Qs, *query_masks.shape[2:])
+        if self._wants_grad():
+            (mask, flags) = self._forward_train(input_frames, flat_q, Qs)
+        else:
+            (mask, flags) = self.engine().forward(self, input_frames, flat_q, queries_per_video=Qs)
         mask = mask.reshape(B, Qs, *mask.shape[1:])
         if flags is not None:
             flags = flags.reshape(B, Qs, *flags.shape[1:])

@@ -101,3 +101,31 @@ def make_clip(sample, num_frames=30, frame_height=240, frame_width=320, query_fr
 def make_batch(samples, **kw):
     clips = [make_clip(s, **kw) for s in samples]
     return torch.stack([c[0] for c in clips]), torch.stack([c[1] for c in clips])
+
+
+def make_targets(samples, num_frames=30, frame_height=240, frame_width=320, output_channels=3, flag_channels=3):
+    """Seeded binary mask / flag targets for the training-step parity tests and benchmark
+    (stand-in for the Kubric ground truth consumed by loss.py:164-225)."""
+    masks, flags = [], []
+    for s in samples:
+        g = torch.Generator().manual_seed(5000 + s)
+        m = torch.zeros(output_channels, num_frames, frame_height, frame_width)
+        for c in range(output_channels):
+            h, w = max(frame_height // (3 + c), 1), max(frame_width // (4 + c), 1)
+            for t in range(num_frames):
+                y0 = int(torch.randint(0, frame_height - h + 1, (1,), generator=g))
+                x0 = int(torch.randint(0, frame_width - w + 1, (1,), generator=g))
+                m[c, t, y0:y0 + h, x0:x0 + w] = 1.0
+        masks.append(m)
+        flags.append((torch.rand(num_frames, max(flag_channels, 1), generator=g) > 0.5).float())
+    return torch.stack(masks), torch.stack(flags)[..., :flag_channels]
+
+
+def training_loss(output_mask, output_flags, target_mask, target_flags):
+    """Mean BCE-with-logits on the mask logits plus mean BCE on the flag logits: the differentiable core of
+    loss.py:164-225 (the reference adds weighting / top-k bootstrapping on top of exactly these terms)."""
+    import torch.nn.functional as F
+    loss = F.binary_cross_entropy_with_logits(output_mask, target_mask)
+    if output_flags is not None and output_flags.numel() > 0:
+        loss = loss + F.binary_cross_entropy_with_logits(output_flags, target_flags)
+    return loss
