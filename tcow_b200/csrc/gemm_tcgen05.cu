@@ -122,6 +122,35 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x * 0.3989422804014327f, e, Phi);
 }
 
+// Packed-fp32x2 form of dgelu_erf for the DGELU epilogue (two values per issue slot, one MUFU each).
+__device__ __forceinline__ uint64_t dgelu_erf2(float x0, float x1) {
+  const float n0 = fmaxf(-fabsf(x0), -5.75f), n1 = fmaxf(-fabsf(x1), -5.75f);
+  const uint64_t na = f2_pack(n0, n1);
+  uint64_t q = f2_pack(1.740049385e-07f, 1.740049385e-07f);
+  q = f2_fma(q, na, f2_pack(5.850045000e-06f, 5.850045000e-06f));
+  q = f2_fma(q, na, f2_pack(8.705152140e-05f, 8.705152140e-05f));
+  q = f2_fma(q, na, f2_pack(7.601087564e-04f, 7.601087564e-04f));
+  q = f2_fma(q, na, f2_pack(4.371289164e-03f, 4.371289164e-03f));
+  q = f2_fma(q, na, f2_pack(1.773692295e-02f, 1.773692295e-02f));
+  q = f2_fma(q, na, f2_pack(5.366283283e-02f, 5.366283283e-02f));
+  q = f2_fma(q, na, f2_pack(1.275363415e-01f, 1.275363415e-01f));
+  q = f2_fma(q, na, f2_pack(2.482131273e-01f, 2.482131273e-01f));
+  q = f2_fma(q, na, f2_pack(3.987075090e-01f, 3.987075090e-01f));
+  q = f2_fma(q, na, f2_pack(4.999948144e-01f, 4.999948144e-01f));
+  const uint64_t w = f2_mul(na, f2_pack(0.84932180028801904f, 0.84932180028801904f));
+  float ww0, ww1;
+  f2_unpack(f2_mul(w, w), ww0, ww1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-ww0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-ww1));
+  const uint64_t e = f2_pack(e0, e1);
+  // Phi = 0.5 + sign(x) * (0.5 - h),  h = q e
+  const uint64_t half = f2_pack(0.5f, 0.5f);
+  const uint64_t t = f2_fma(f2_mul(q, e), f2_pack(-1.f, -1.f), half);
+  const uint64_t Phi = f2_fma(f2_pack(copysignf(1.f, x0), copysignf(1.f, x1)), t, half);
+  return f2_fma(f2_mul(f2_pack(x0, x1), f2_pack(0.3989422804014327f, 0.3989422804014327f)), e, Phi);
+}
+
 // LayerNorm tail of the residual epilogue (EPI_F32_ADD_LN): once a warp's TMA reduce-adds for ALL column tiles of its
 // 32 rows have completed, the rows of the updated fp32 stream are complete in L2; the warp reads them back (L2 hits,
 // they were just written), normalises with fp32 statistics and writes the bf16 operand of the NEXT GEMM — the
@@ -444,8 +473,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  f[2 * e] *= dgelu_erf(__uint_as_float(zw[e] << 16));
-                  f[2 * e + 1] *= dgelu_erf(__uint_as_float(zw[e] & 0xffff0000u));
+                  const uint64_t dg = dgelu_erf2(__uint_as_float(zw[e] << 16), __uint_as_float(zw[e] & 0xffff0000u));
+                  f2_unpack(f2_mul(f2_pack(f[2 * e], f[2 * e + 1]), dg), f[2 * e], f[2 * e + 1]);
                 }
               }
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + srow + ((j ^ sw) << 4)),

@@ -11,7 +11,7 @@ namespace tcow {
 
 namespace {
 constexpr int LNB_MAX_BLOCKS = 592;   // 4 x 148
-constexpr int CS_MAX_CHUNKS = 64;
+constexpr int CS_MAX_CHUNKS = 256;
 
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -63,80 +63,107 @@ __global__ void __launch_bounds__(256) layernorm_train_kernel(const float* __res
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;   G (+)= dx;  Gb = bf16(G)
 // per-block partial sums of dgamma = sum_rows dy*xhat and dbeta = sum_rows dy -> partial[block][2][D]
-template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                            const __nv_bfloat16* __restrict__ xhat,
-                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                            float* __restrict__ G, __nv_bfloat16* __restrict__ Gb,
-                                                            float* __restrict__ partial, int rows, int accumulate) {
-  constexpr int D = NV * 128;
-  __shared__ float s_red[8][2][128];  // one 128-column group (NV index) at a time
+// One warp per row; lane l owns the 8-column groups (v*32+l)*8 .. +8 (16-byte bf16 vectors, 2 x float4 of G).  dy / xhat
+// stay packed in registers and the G row is requested together with them, so that all of a row's HBM latency is paid
+// once; the kernel is limited to 128 registers (two 8-warp blocks per SM).
+template <int NV>  // D = NV * 256
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ xhat,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               float* __restrict__ G, __nv_bfloat16* __restrict__ Gb,
+                                                               float* __restrict__ partial, int rows, int accumulate) {
+  constexpr int D = NV * 256;
+  __shared__ float s_red[8][2][256];  // one 256-column group (vector index) at a time
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_grid = gridDim.x * 8;
-  float dg[NV][4], db[NV][4];
+  float dg[NV][8], db[NV][8];
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) dg[i][e] = db[i][e] = 0.f;
-  float4 gm[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    for (int e = 0; e < 8; ++e) dg[v][e] = db[v][e] = 0.f;
+  const float4* gm4 = reinterpret_cast<const float4*>(gamma);
   for (int row = blockIdx.x * 8 + warp; row < rows; row += warps_per_grid) {
-    const uint2* dr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
-    const uint2* hr = reinterpret_cast<const uint2*>(xhat + static_cast<size_t>(row) * D);
-    float d[NV][4], h[NV][4];
+    const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * D);
+    const uint4* hr = reinterpret_cast<const uint4*>(xhat + static_cast<size_t>(row) * D);
+    float4* gr = reinterpret_cast<float4*>(G + static_cast<size_t>(row) * D);
+    uint4 a[NV], b[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      a[v] = __ldcs(dr + v * 32 + lane);
+      b[v] = __ldcs(hr + v * 32 + lane);
+    }
+    if (accumulate) {  // pull the G row towards L2 now; it is read after the row statistics
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gr + (v * 32 + lane) * 2));
+    }
+    const float rs = __ldg(rstd + row);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const uint2 a = __ldcs(dr + i * 32 + lane), b = __ldcs(hr + i * 32 + lane);
-      d[i][0] = bf_lo(a.x); d[i][1] = bf_hi(a.x); d[i][2] = bf_lo(a.y); d[i][3] = bf_hi(a.y);
-      h[i][0] = bf_lo(b.x); h[i][1] = bf_hi(b.x); h[i][2] = bf_lo(b.y); h[i][3] = bf_hi(b.y);
-      const float g4[4] = {gm[i].x, gm[i].y, gm[i].z, gm[i].w};
+    for (int v = 0; v < NV; ++v) {
+      const uint32_t aw[4] = {a[v].x, a[v].y, a[v].z, a[v].w}, bw[4] = {b[v].x, b[v].y, b[v].z, b[v].w};
+      const float4 g0 = __ldg(gm4 + (v * 32 + lane) * 2), g1 = __ldg(gm4 + (v * 32 + lane) * 2 + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        dg[i][e] = fmaf(d[i][e], h[i][e], dg[i][e]);
-        db[i][e] += d[i][e];
-        d[i][e] *= g4[e];  // g = dy * gamma
-        s1 += d[i][e];
-        s2 = fmaf(d[i][e], h[i][e], s2);
+        const float d0 = bf_lo(aw[e]), d1 = bf_hi(aw[e]), h0 = bf_lo(bw[e]), h1 = bf_hi(bw[e]);
+        dg[v][2 * e] = fmaf(d0, h0, dg[v][2 * e]);
+        dg[v][2 * e + 1] = fmaf(d1, h1, dg[v][2 * e + 1]);
+        db[v][2 * e] += d0;
+        db[v][2 * e + 1] += d1;
+        const float q0 = d0 * gg[2 * e], q1 = d1 * gg[2 * e + 1];  // g = dy * gamma
+        s1 += q0 + q1;
+        s2 = fmaf(q0, h0, fmaf(q1, h1, s2));
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o2);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
     }
-    const float c1 = s1 * (1.0f / D), c2 = s2 * (1.0f / D), rs = __ldg(rstd + row);
-    float4* gr = reinterpret_cast<float4*>(G + static_cast<size_t>(row) * D);
-    uint2* br = reinterpret_cast<uint2*>(Gb + static_cast<size_t>(row) * D);
+    const float c1 = s1 * (1.0f / D), c2 = s2 * (1.0f / D);
+    uint4* br = reinterpret_cast<uint4*>(Gb + static_cast<size_t>(row) * D);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float4 o = accumulate ? gr[i * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-      o.x += rs * (d[i][0] - c1 - h[i][0] * c2);
-      o.y += rs * (d[i][1] - c1 - h[i][1] * c2);
-      o.z += rs * (d[i][2] - c1 - h[i][2] * c2);
-      o.w += rs * (d[i][3] - c1 - h[i][3] * c2);
-      gr[i * 32 + lane] = o;
-      br[i * 32 + lane] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    for (int v = 0; v < NV; ++v) {
+      const uint32_t aw[4] = {a[v].x, a[v].y, a[v].z, a[v].w}, bw[4] = {b[v].x, b[v].y, b[v].z, b[v].w};
+      const float4 g0 = __ldg(gm4 + (v * 32 + lane) * 2), g1 = __ldg(gm4 + (v * 32 + lane) * 2 + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float r[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h0 = bf_lo(bw[e]), h1 = bf_hi(bw[e]);
+        r[2 * e] = rs * (bf_lo(aw[e]) * gg[2 * e] - c1 - h0 * c2);
+        r[2 * e + 1] = rs * (bf_hi(aw[e]) * gg[2 * e + 1] - c1 - h1 * c2);
+      }
+      float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+      if (accumulate) {
+        o0 = gr[(v * 32 + lane) * 2];
+        o1 = gr[(v * 32 + lane) * 2 + 1];
+      }
+      o0.x += r[0]; o0.y += r[1]; o0.z += r[2]; o0.w += r[3];
+      o1.x += r[4]; o1.y += r[5]; o1.z += r[6]; o1.w += r[7];
+      gr[(v * 32 + lane) * 2] = o0;
+      gr[(v * 32 + lane) * 2 + 1] = o1;
+      br[v * 32 + lane] = make_uint4(pack_bf16(o0.x, o0.y), pack_bf16(o0.z, o0.w), pack_bf16(o1.x, o1.y), pack_bf16(o1.z, o1.w));
     }
   }
-  // block reduction of the per-warp column sums, one 128-column group (NV index) at a time
+  // block reduction of the per-warp column sums, one 256-column group at a time
   float* pg = partial + static_cast<size_t>(blockIdx.x) * 2 * D;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int v = 0; v < NV; ++v) {
     __syncthreads();
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      s_red[warp][0][lane * 4 + e] = dg[i][e];
-      s_red[warp][1][lane * 4 + e] = db[i][e];
+    for (int e = 0; e < 8; ++e) {
+      s_red[warp][0][lane * 8 + e] = dg[v][e];
+      s_red[warp][1][lane * 8 + e] = db[v][e];
     }
     __syncthreads();
-    if (threadIdx.x < 256) {
-      const int which = threadIdx.x >> 7, col = threadIdx.x & 127;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += s_red[w][which][col];
-      pg[which * D + i * 128 + col] = s;
+      for (int w = 0; w < 8; ++w) s += s_red[w][which][threadIdx.x];
+      pg[which * D + v * 256 + threadIdx.x] = s;
     }
   }
 }
@@ -163,8 +190,20 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col0 < N) {
-    for (int r = r0 + warp; r < r1; r += 8) {
-      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ld + col0));
+    const __nv_bfloat16* xc = x + col0;
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {  // four independent 16-byte loads in flight per lane
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const uint4*>(xc + static_cast<int64_t>(r + 8 * u) * ld));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf_lo(v[u].x); acc[1] += bf_hi(v[u].x); acc[2] += bf_lo(v[u].y); acc[3] += bf_hi(v[u].y);
+        acc[4] += bf_lo(v[u].z); acc[5] += bf_hi(v[u].z); acc[6] += bf_lo(v[u].w); acc[7] += bf_hi(v[u].w);
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xc + static_cast<int64_t>(r) * ld));
       acc[0] += bf_lo(v.x); acc[1] += bf_hi(v.x); acc[2] += bf_lo(v.y); acc[3] += bf_hi(v.y);
       acc[4] += bf_lo(v.z); acc[5] += bf_hi(v.z); acc[6] += bf_lo(v.w); acc[7] += bf_hi(v.w);
     }
@@ -326,7 +365,7 @@ static int launch_ln_train(const float* x, const float* g, const float* b, void*
 template <int NV>
 static int launch_ln_bwd(const void* dy, const void* xhat, const float* rstd, const float* gamma, float* G, void* Gb,
                          float* dgamma, float* dbeta, float* ws, int rows, int accumulate, cudaStream_t s) {
-  constexpr int D = NV * 128;
+  constexpr int D = NV * 256;
   int blocks = (rows + 7) / 8;
   if (blocks > LNB_MAX_BLOCKS) blocks = LNB_MAX_BLOCKS;
   layernorm_bwd_kernel<NV><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(xhat),
@@ -343,7 +382,7 @@ static int launch_ln_bwd(const void* dy, const void* xhat, const float* rstd, co
 extern "C" int64_t tcow_train_workspace_floats(int max_cols) {
   // the largest of: LayerNorm bwd partials (blocks x 2 x D), column-sum partials (chunks x N), time-embed partials
   const int64_t a = static_cast<int64_t>(tcow::LNB_MAX_BLOCKS) * 2 * 1024;
-  const int64_t b = static_cast<int64_t>(tcow::CS_MAX_CHUNKS) * (max_cols > 0 ? max_cols : 4096);
+  const int64_t b = static_cast<int64_t>(tcow::CS_MAX_CHUNKS) * (max_cols > 0 ? max_cols : 4096);  // colsum: chunks x N
   return a > b ? a : b;
 }
 
@@ -367,8 +406,8 @@ extern "C" int tcow_layernorm_bwd(const void* dy, const void* xhat, const float*
     return set_error(TCOW_ERR_ARG, "layernorm_bwd: bad argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (D) {
-    case 768: return launch_ln_bwd<6>(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, rows, accumulate, s);
-    case 1024: return launch_ln_bwd<8>(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, rows, accumulate, s);
+    case 768: return launch_ln_bwd<3>(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, rows, accumulate, s);
+    case 1024: return launch_ln_bwd<4>(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, rows, accumulate, s);
   }
   return set_error(TCOW_ERR_ARG, "layernorm_bwd: unsupported width %d (768 or 1024)", D);
 }
@@ -379,8 +418,13 @@ extern "C" int tcow_colsum_bf16(const void* x, int64_t ldx, int rows, int N, flo
   if (!x || !out || !workspace || rows <= 0 || N <= 0) return set_error(TCOW_ERR_ARG, "colsum: bad argument");
   if ((N % 8) || (ldx % 8) || (reinterpret_cast<uintptr_t>(x) & 15)) return set_error(TCOW_ERR_ARG, "colsum: N and pitch must be multiples of 8");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int chunks = (rows + 255) / 256;
+  // ~8 blocks per SM over (column groups x row chunks), at least 64 rows per chunk
+  const int colgroups = (N + 255) / 256;
+  int chunks = (8 * sm_count() + colgroups - 1) / colgroups;
+  if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
   if (chunks > CS_MAX_CHUNKS) chunks = CS_MAX_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  if (static_cast<int64_t>(chunks) * N > tcow_train_workspace_floats(N)) return set_error(TCOW_ERR_ARG, "colsum: workspace too small");
   colsum_bf16_kernel<<<dim3((N + 255) / 256, chunks), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, rows, N, workspace);
   int rc = check_launch("colsum_bf16_kernel");
   if (rc) return rc;

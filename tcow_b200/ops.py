@@ -185,7 +185,7 @@ def layernorm_bwd(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, accumu
 def colsum(x, out, workspace, accumulate=True):
     _chk(x, torch.bfloat16, 'colsum.x'); _chk(out, torch.float32, 'colsum.out')
     rows, N = x.shape
-    if out.numel() != N or workspace.numel() < 64 * N:
+    if out.numel() != N or workspace.numel() < 256 * N:
         raise ValueError('colsum: output / workspace size mismatch')
     _lib.call('tcow_colsum_bf16', x.data_ptr(), x.stride(0), rows, N, out.data_ptr(), workspace.data_ptr(),
               int(accumulate), _stream())
