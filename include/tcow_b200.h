@@ -40,6 +40,7 @@ extern "C" {
 #define TCOW_EPI_F32_ADD 3   /* C(fp32) += A W^T + bias   (proj/temporal_fc/fc2 + residual: vit.py:176,215-216) */
 #define TCOW_EPI_F32_ADD_LN 4 /* internal: F32_ADD followed by the LayerNorm tail of tcow_gemm_bf16_add_ln */
 #define TCOW_EPI_BF16_GELU_AUX 5 /* training fc1: aux(bf16) = z = A W^T + bias and C(bf16) = gelu_erf(z) (vit.py:55-56) */
+#define TCOW_EPI_F32_ADD_SCALED 7 /* internal: the stochastic-depth residual epilogue of tcow_gemm_bf16_add_scaled     */
 #define TCOW_EPI_BF16_DGELU 6    /* backward of the above: C(bf16) = (A W^T) * gelu_erf'(aux)                      */
 
 /* Library / device checks. */
@@ -134,6 +135,17 @@ int tcow_flag_mean(const float* low, int64_t ld_low, float* flags, int B, int N,
  *  TCOW_EPI_BF16_DGELU:    C = (A W^T) * gelu_erf'(aux)                    (dZ = (dY W2) o gelu'(z), bias must be NULL) */
 int tcow_gemm_bf16_aux(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
                        void* aux, int64_t ldaux, int M, int N, int K, int epilogue, void* stream);
+
+/* Residual GEMM under stochastic depth (DropPath, vit_utils.py:139-164 as applied at vit.py:172,186,216):
+ *   X[r,:] (fp32) += row_scale[r] * (A W^T)[r,:] + bias_scale[r] * bias + bias2
+ * row_scale / bias_scale: fp32 [M] (0 or 1/keep_prob per dropped / kept sequence); bias2 may be NULL. */
+int tcow_gemm_bf16_add_scaled(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                              const float* bias2, const float* row_scale, const float* bias_scale, float* X, int64_t ldx,
+                              int M, int N, int K, void* stream);
+
+/* out[r,:] (bf16) = scale[r] * x[r,:] (bf16): the branch gradient under stochastic depth. */
+int tcow_scale_rows_bf16(const void* x, int64_t ldx, const float* scale, void* out, int64_t ld_out, int rows, int N,
+                         void* stream);
 
 /* Weight gradient of nn.Linear:  dW[N1,N2] (fp32) += A[R,N1]^T (bf16) x B[R,N2] (bf16), contraction over the R
  * token rows (A = dY, B = the layer input).  tcgen05 with both operands MN-major (no transposes in memory), split

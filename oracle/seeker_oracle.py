@@ -33,10 +33,13 @@ TIMESFORMER_STD = 0.225   # model/vision_tf.py:24
 def seeker_forward(sd, input_frames, query_mask, *, causal_attention=1, patch_size=16,
                    num_heads=12, depth=12, track_map_stride=4, track_map_resize='bilinear',
                    output_channels=3, flag_channels=3, norm_embeddings=False,
-                   pretrained_norm=False, eps=1e-6):
+                   pretrained_norm=False, eps=1e-6, drop_path=None):
     """Return (output_mask (B,C,T,Hf,Wf) fp32 logits, output_flags (B,T,F) fp32 or None).
 
     ``sd`` is ``Seeker.state_dict()`` (251 tensors, layout of SURVEY.md §8b).
+    ``drop_path`` (training mode only): per block ``None`` or ``dict(t=(B*N,), s=(B*T,), m=(B,))`` of 0/1 keep masks
+    plus ``keep`` (the keep probability) — DropPath of vit_utils.py:139-164 with the draws made explicit: each branch
+    output is multiplied by mask/keep along its leading dim (vit.py:172 (b h w), :186 (b t), :216 b).
     """
     g = lambda k: sd[PREFIX + k].to(torch.float32)
     P = patch_size
@@ -86,29 +89,35 @@ def seeker_forward(sd, input_frames, query_mask, *, causal_attention=1, patch_si
         o = (attn @ w).transpose(1, 2).reshape(Bn, S, C)
         return lin(o, p + '.proj')
 
+    def dpath(v, i, which):                                            # vit_utils.py:139-164
+        if drop_path is None or drop_path[i] is None:
+            return v
+        m = drop_path[i][which].to(v.dtype).reshape(-1, *([1] * (v.dim() - 1)))
+        return v.div(drop_path[i]['keep']) * m
+
     for i in range(depth):                                             # vit.py:165-217
         b = f'blocks.{i}.'
         xt = x[:, 1:, :].reshape(B * N, T, D)
-        rt = attention(ln(xt, b + 'temporal_norm1'), b + 'temporal_attn', causal_attention)
+        rt = dpath(attention(ln(xt, b + 'temporal_norm1'), b + 'temporal_attn', causal_attention), i, 't')
         rt = lin(rt.reshape(B, N * T, D), b + 'temporal_fc')
         xt = x[:, 1:, :] + rt
         init_cls = x[:, 0, :].unsqueeze(1)
         xs = xt.reshape(B, N, T, D).permute(0, 2, 1, 3).reshape(B * T, N, D)
         if causal_attention in (0, 1):
             c = init_cls.repeat(1, T, 1).reshape(B * T, 1, D)
-            rs = attention(ln(torch.cat([c, xs], 1), b + 'norm1'), b + 'attn', 0)
+            rs = dpath(attention(ln(torch.cat([c, xs], 1), b + 'norm1'), b + 'attn', 0), i, 's')
             c = rs[:, 0, :].reshape(B, T, D)
             c = c.mean(1, keepdim=True) if causal_attention == 0 else c[:, 0:1, :]
             rs = rs[:, 1:, :]
         elif causal_attention >= 2 or causal_attention == -1:
             c = torch.zeros_like(init_cls)
-            rs = attention(ln(xs, b + 'norm1'), b + 'attn', 0)
+            rs = dpath(attention(ln(xs, b + 'norm1'), b + 'attn', 0), i, 's')
         else:
             raise ValueError(causal_attention)
         rs = rs.reshape(B, T, N, D).permute(0, 2, 1, 3).reshape(B, N * T, D)
         x = torch.cat([init_cls, xt], 1) + torch.cat([c, rs], 1)
         h = F.gelu(lin(ln(x, b + 'norm2'), b + 'mlp.fc1'))             # nn.GELU() = exact erf
-        x = x + lin(h, b + 'mlp.fc2')
+        x = x + dpath(lin(h, b + 'mlp.fc2'), i, 'm')
 
     if norm_embeddings:                                                # vision_tf.py:152-153
         x = ln(x, 'norm')

@@ -39,6 +39,9 @@ SIGNATURES = {
     # ---- training step
     'tcow_gemm_bf16_aux': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                            c_int, c_int, c_int, c_int, c_void_p],
+    'tcow_gemm_bf16_add_scaled': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int64, c_int, c_int, c_int, c_void_p],
+    'tcow_scale_rows_bf16': [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
     'tcow_gemm_bf16_wgrad': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     'tcow_train_workspace_floats': [c_int],
     'tcow_layernorm_bf16_train': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,

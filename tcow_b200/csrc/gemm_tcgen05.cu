@@ -28,7 +28,8 @@ struct GemmCfg {
   static constexpr bool PAIR = (CL == 3);
   static constexpr int CSIZE = (CL == 1) ? 1 : 2;   // CTAs per cluster
   static constexpr bool LN_TAIL = (EPI == TCOW_EPI_F32_ADD_LN);
-  static constexpr bool RED_ADD = (EPI == TCOW_EPI_F32_ADD || LN_TAIL);
+  static constexpr bool SCALED = (EPI == TCOW_EPI_F32_ADD_SCALED);  // stochastic depth: per-row scale of the branch
+  static constexpr bool RED_ADD = (EPI == TCOW_EPI_F32_ADD || LN_TAIL || SCALED);
   static constexpr bool OUT_F32 = (EPI == TCOW_EPI_F32_STORE || RED_ADD);
   // training epilogues: GELU_AUX also stores the pre-activation (second TMA store through tmAux); DGELU multiplies
   // the accumulator by gelu'(z), z read from the saved pre-activation
@@ -155,6 +156,14 @@ __device__ __forceinline__ uint64_t dgelu_erf2(float x0, float x1) {
 // 32 rows have completed, the rows of the updated fp32 stream are complete in L2; the warp reads them back (L2 hits,
 // they were just written), normalises with fp32 statistics and writes the bf16 operand of the NEXT GEMM — the
 // separate LayerNorm pass over HBM (vit.py:135,142,150) disappears.  gamma == nullptr: plain bf16 cast.
+// Stochastic-depth form of the residual epilogue (DropPath, vit_utils.py:139-164 applied at vit.py:172,186,216):
+//   X[r,:] += row_scale[r] * acc[r,:] + bias_scale[r] * bias + bias2
+struct RowScale {
+  const float* row_scale;
+  const float* bias_scale;
+  const float* bias2;
+};
+
 struct LnTail {
   const float* x;        // the fp32 stream the GEMM accumulates into (C)
   int64_t ldx;
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI, CL>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
                     const LnTail ln, const __grid_constant__ CUtensorMap tmAux, const __nv_bfloat16* __restrict__ aux,
-                    int64_t ldaux) {
+                    int64_t ldaux, const RowScale rsc) {
   using Cfg = GemmCfg<BN, EPI, CL>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool PAIR = Cfg::PAIR;
@@ -418,14 +427,30 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (PAIR) mbar_arrive_cluster(tempty_bar(acc), 0);  // the pair's MMA issuer lives in the leader CTA
             else mbar_arrive(tempty_bar(acc));
           }
+          float row_s = 1.f, bias_s = 1.f;
+          if constexpr (Cfg::SCALED) {
+            const int grow = m_blk * BM + ew * 32 + lane;
+            if (grow < M) {
+              row_s = __ldg(rsc.row_scale + grow);
+              bias_s = __ldg(rsc.bias_scale + grow);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + j) : make_float4(0, 0, 0, 0);
             float4 o;
+            if constexpr (Cfg::SCALED) {
+              const float4 b2 = rsc.bias2 ? __ldg(reinterpret_cast<const float4*>(rsc.bias2 + col0) + j) : make_float4(0, 0, 0, 0);
+              o.x = fmaf(row_s, __uint_as_float(v[4 * j + 0]), fmaf(bias_s, b.x, b2.x));
+              o.y = fmaf(row_s, __uint_as_float(v[4 * j + 1]), fmaf(bias_s, b.y, b2.y));
+              o.z = fmaf(row_s, __uint_as_float(v[4 * j + 2]), fmaf(bias_s, b.z, b2.z));
+              o.w = fmaf(row_s, __uint_as_float(v[4 * j + 3]), fmaf(bias_s, b.w, b2.w));
+            } else {
             o.x = __uint_as_float(v[4 * j + 0]) + b.x;
             o.y = __uint_as_float(v[4 * j + 1]) + b.y;
             o.z = __uint_as_float(v[4 * j + 2]) + b.z;
             o.w = __uint_as_float(v[4 * j + 3]) + b.w;
+            }
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + srow + ((j ^ sw) << 4)), "f"(o.x),
                          "f"(o.y), "f"(o.z), "f"(o.w)
                          : "memory");
@@ -561,7 +586,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 template <int BN, int EPI, int CL>
 static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream, const LnTail& ln = LnTail{},
-                       const void* aux = nullptr, int64_t ldaux = 0) {
+                       const void* aux = nullptr, int64_t ldaux = 0, const RowScale& rsc = RowScale{}) {
   using Cfg = GemmCfg<BN, EPI, CL>;
   constexpr int CS = Cfg::CSIZE;
   alignas(64) CUtensorMap tmA, tmB, tmC;
@@ -597,7 +622,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, bias, M, N, K, ln, tmAux,
-                                     static_cast<const __nv_bfloat16*>(aux), ldaux);
+                                     static_cast<const __nv_bfloat16*>(aux), ldaux, rsc);
   if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "gemm_bf16_tn_kernel: launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_tn_kernel");
 }
@@ -616,17 +641,17 @@ static int cluster_mode(int M, int epi) {
 template <int EPI>
 static int dispatch_bn(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream, const void* aux = nullptr,
-                       int64_t ldaux = 0) {
+                       int64_t ldaux = 0, const RowScale& rsc = RowScale{}) {
   const LnTail none{};
   if (N % 256 == 0) {
     switch (cluster_mode(M, EPI)) {
-      case 3: return launch_gemm<256, EPI, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
-      case 2: return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
-      default: return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
+      case 3: return launch_gemm<256, EPI, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
+      case 2: return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
+      default: return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
     }
   }
-  if (N % 128 == 0) return launch_gemm<128, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
-  return launch_gemm<64, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux);
+  if (N % 128 == 0) return launch_gemm<128, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
+  return launch_gemm<64, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
 }
 
 }  // namespace tcow
@@ -668,6 +693,21 @@ extern "C" int tcow_gemm_bf16_aux(const void* A, int64_t lda, const void* W, int
       return dispatch_bn<TCOW_EPI_BF16_DGELU>(A, lda, W, ldw, bias, C, ldc, M, N, K, s, aux, ldaux);
   }
   return set_error(TCOW_ERR_ARG, "gemm_aux: epilogue %d takes no auxiliary tensor", epilogue);
+}
+
+extern "C" int tcow_gemm_bf16_add_scaled(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                         const float* bias2, const float* row_scale, const float* bias_scale, float* X,
+                                         int64_t ldx, int M, int N, int K, void* stream) {
+  using namespace tcow;
+  if (!A || !W || !X || !row_scale || !bias_scale) return set_error(TCOW_ERR_ARG, "gemm_add_scaled: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(TCOW_ERR_ARG, "gemm_add_scaled: non-positive dimension");
+  if (N % 64 != 0 || K % 64 != 0)
+    return set_error(TCOW_ERR_ARG, "gemm_add_scaled: N (%d) and K (%d) must be multiples of 64", N, K);
+  if ((bias && (reinterpret_cast<uintptr_t>(bias) & 15)) || (bias2 && (reinterpret_cast<uintptr_t>(bias2) & 15)))
+    return set_error(TCOW_ERR_ARG, "gemm_add_scaled: biases must be 16-byte aligned");
+  const RowScale rsc{row_scale, bias_scale, bias2};
+  return dispatch_bn<TCOW_EPI_F32_ADD_SCALED>(A, lda, W, ldw, bias, X, ldx, M, N, K, static_cast<cudaStream_t>(stream),
+                                              nullptr, 0, rsc);
 }
 
 extern "C" int tcow_gemm_bf16_add_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* X,

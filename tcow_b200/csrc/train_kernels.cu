@@ -220,6 +220,20 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+// out[r, :] = scale[r] * x[r, :]  (bf16, 8 columns per thread)
+__global__ void scale_rows_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ scale,
+                                       __nv_bfloat16* __restrict__ out, int64_t ldo, int rows, int nvec) {
+  const int64_t total = static_cast<int64_t>(rows) * nvec;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / nvec), c = static_cast<int>(i % nvec);
+    const float s = __ldg(scale + r);
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(x + r * ldx) + c);
+    reinterpret_cast<uint4*>(out + r * ldo)[c] =
+        make_uint4(pack_bf16(s * bf_lo(v.x), s * bf_hi(v.x)), pack_bf16(s * bf_lo(v.y), s * bf_hi(v.y)),
+                   pack_bf16(s * bf_lo(v.z), s * bf_hi(v.z)), pack_bf16(s * bf_lo(v.w), s * bf_hi(v.w)));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- embedding gradients
 // dpos[1+n, :] (+)= sum_{b,t} G[(b*N+n)*T+t, :]   (block per n, float4 per thread)
 __global__ void embed_bwd_pos_kernel(const float* __restrict__ G, float* __restrict__ dpos, int B, int N, int T, int D,
@@ -482,4 +496,18 @@ extern "C" int tcow_cls_merge_bwd(const void* d_out, int64_t ld_out, float* d_ou
   cls_merge_bwd_kernel<<<B * T, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(d_out), ld_out, d_out_cls, B, T, D,
                                                                          cls_row0, mode);
   return check_launch("cls_merge_bwd_kernel");
+}
+
+extern "C" int tcow_scale_rows_bf16(const void* x, int64_t ldx, const float* scale, void* out, int64_t ld_out, int rows,
+                                    int N, void* stream) {
+  using namespace tcow;
+  if (!x || !scale || !out || rows <= 0 || N <= 0) return set_error(TCOW_ERR_ARG, "scale_rows: bad argument");
+  if ((N % 8) || (ldx % 8) || (ld_out % 8)) return set_error(TCOW_ERR_ARG, "scale_rows: N and pitches must be multiples of 8");
+  const int64_t total = static_cast<int64_t>(rows) * (N / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  scale_rows_bf16_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, scale, static_cast<__nv_bfloat16*>(out), ld_out, rows, N / 8);
+  return check_launch("scale_rows_bf16_kernel");
 }

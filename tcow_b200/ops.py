@@ -237,3 +237,27 @@ def attn_spatial_bwd(qkv, out, out_cls, d_out, d_out_cls, lse, d_qkv, d_cls, B, 
 def cls_merge_bwd(d_out, d_out_cls, B, T, D, cls_row0, mode):
     _lib.call('tcow_cls_merge_bwd', d_out.data_ptr(), d_out.stride(0), d_out_cls.data_ptr(), B, T, D, cls_row0, mode,
               _stream())
+
+
+def gemm_add_scaled(a, w, bias, bias2, row_scale, bias_scale, x):
+    """x[M,N] (fp32) += row_scale[:,None] * (a @ w^T) + bias_scale[:,None] * bias + bias2   (stochastic depth)."""
+    _chk(a, torch.bfloat16, 'gemm_add_scaled.a'); _chk(w, torch.bfloat16, 'gemm_add_scaled.w')
+    _chk(x, torch.float32, 'gemm_add_scaled.x'); _chk(row_scale, torch.float32, 'gemm_add_scaled.row_scale')
+    _chk(bias_scale, torch.float32, 'gemm_add_scaled.bias_scale')
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or tuple(x.shape) != (M, N) or row_scale.numel() < M or bias_scale.numel() < M:
+        raise ValueError('gemm_add_scaled: shape mismatch')
+    _lib.call('tcow_gemm_bf16_add_scaled', a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _p(bias), _p(bias2),
+              row_scale.data_ptr(), bias_scale.data_ptr(), x.data_ptr(), x.stride(0), M, N, K, _stream())
+    return x
+
+
+def scale_rows(x, scale, out):
+    _chk(x, torch.bfloat16, 'scale_rows.x'); _chk(out, torch.bfloat16, 'scale_rows.out')
+    rows, N = x.shape
+    if tuple(out.shape) != (rows, N) or scale.numel() < rows:
+        raise ValueError('scale_rows: shape mismatch')
+    _lib.call('tcow_scale_rows_bf16', x.data_ptr(), x.stride(0), scale.data_ptr(), out.data_ptr(), out.stride(0), rows, N,
+              _stream())
+    return out

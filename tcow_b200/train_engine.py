@@ -66,7 +66,7 @@ class _GradLayout:
             add(p + 's_proj_w', D, D); add(p + 's_proj_b', D); add(p + 's_qkv_w', 3 * D, D); add(p + 's_qkv_b', 3 * D)
             add(p + 'n1_g', D); add(p + 'n1_b', D)
             if merged:
-                add(p + 't_out_w', D, D); add(p + 't_out_b', D)
+                add(p + 't_out_w', D, D); add(p + 't_out_b', D); add(p + 't_out_b2', D)
             else:
                 add(p + 't_fc_w', D, D); add(p + 't_fc_b', D); add(p + 't_proj_w', D, D); add(p + 't_proj_b', D)
             add(p + 't_qkv_w', 3 * D, D); add(p + 't_qkv_b', 3 * D); add(p + 'tn1_g', D); add(p + 'tn1_b', D)
@@ -96,6 +96,9 @@ class SeekerTrainEngine:
         self.launches = 0
         self.profile = None
         self.grad_sync = None        # optional ddp.GradSync: all-reduces finished ranges of the flat gradient buffer
+        # tests inject fixed stochastic-depth keep masks here: list (one per block) of None or
+        # dict(t=[B*N], s=[B*T], m=[B]) 0/1 tensors; None = draw them (vit_utils.py:139-164)
+        self.drop_path_override = None
         self.last_flat = None
 
     # ------------------------------------------------------------------ plumbing
@@ -148,7 +151,8 @@ class SeekerTrainEngine:
             w.raw_t = (Wp, bp, Wf, bfc)
             if self.merge_temporal_proj:   # fc(proj(o)) = o (Wf Wp)^T + (Wf bp + bf)   (vit.py:111 -> :174, no nonlinearity)
                 Wm = _mm(Wf, Wp)
-                w.t_out = (bf(Wm), (_mm(Wf, bp[:, None])[:, 0] + bfc).contiguous(), bft(Wm))
+                b1 = _mm(Wf, bp[:, None])[:, 0].contiguous()        # the part of the bias that sits inside DropPath
+                w.t_out = (bf(Wm), (b1 + bfc).contiguous(), bft(Wm), b1, bfc.contiguous())
             else:
                 w.t_proj, w.t_fc = lin(blk.temporal_attn.proj), lin(blk.temporal_fc)
             pk.blocks.append(w)
@@ -180,7 +184,7 @@ class SeekerTrainEngine:
         if sc is None:
             e = lambda shape, dt: torch.empty(shape, device=device, dtype=dt)
             sc = dict(X=e((R, D), torch.float32), G=e((R, D), torch.float32), Gb=e((R, D), torch.bfloat16),
-                      dA=e((R, D), torch.bfloat16), dO=e((R, D), torch.bfloat16), dQKV=e((R, 3 * D), torch.bfloat16),
+                      dA=e((R, D), torch.bfloat16), dO=e((R, D), torch.bfloat16), Gs=e((R, D), torch.bfloat16), dQKV=e((R, 3 * D), torch.bfloat16),
                       dZ=e((R, 4 * D), torch.bfloat16), LOW=e((R, n_pad), torch.float32),
                       dLOW=e((R, n_pad), torch.bfloat16), ws=e((ops.train_workspace_floats(4 * D),), torch.float32))
             if len(self._scratch) >= 2:
@@ -188,14 +192,47 @@ class SeekerTrainEngine:
             self._scratch[key] = sc
         return sc
 
+    # ------------------------------------------------------------------ stochastic depth
+    def _drop_path_scales(self, mod, depth, B, N, T, M, R, Rs, use_cls, causal, device):
+        """Per-block row scales of the three residual branches (DropPath, vit_utils.py:139-164): the reference draws one
+        Bernoulli(keep) per leading-dim entry of the branch — (b h w) sequences for the temporal branch, (b t) frames for
+        the spatial one, b samples for the MLP (vit.py:170-172, 181-186, 216) — and scales survivors by 1/keep; rates are
+        linspace(0, drop_path_rate, depth) (vit.py:272-273), block 0 has none."""
+        rate = float(mod.drop_path_rate)
+        if not (mod.training and rate > 0.0) and self.drop_path_override is None:
+            return None
+        rates = torch.linspace(0, rate, depth).tolist()
+        out = []
+        for i in range(depth):
+            ov = None if self.drop_path_override is None else self.drop_path_override[i]
+            if ov is None and (self.drop_path_override is not None or rates[i] == 0.0):
+                out.append(None)
+                continue
+            keep = 1.0 - rates[i]
+            if ov is not None:
+                keep = float(ov.get('keep', keep))
+                mt, ms, mm = (ov[k].to(device=device, dtype=torch.float32) for k in ('t', 's', 'm'))
+            else:
+                mt, ms, mm = (torch.floor(keep + torch.rand(n, device=device)) for n in (B * N, B * T, B))
+            st, ss, sm = mt / keep, ms / keep, mm / keep
+            rs_t = st.repeat_interleave(T).contiguous()
+            rs_s = ss.view(B, 1, T).expand(B, N, T).reshape(M)
+            bs_s = rs_s
+            if use_cls:
+                if causal == 1:      # only frame 0's cls output is used (vit.py:198)
+                    c = ss.view(B, T)[:, 0]
+                    rs_s, bs_s = torch.cat([rs_s, c]), torch.cat([rs_s, c])
+                else:                # the mean over frames is taken after DropPath: the matmul part is pre-weighted
+                    rs_s, bs_s = torch.cat([rs_s, torch.ones(B, device=device)]), torch.cat([rs_s, ss.view(B, T).mean(1)])
+            rs_m = torch.cat([sm.repeat_interleave(N * T), sm])
+            out.append(dict(rs_t=rs_t, rs_s=rs_s.contiguous(), bs_s=bs_s.contiguous(), rs_m=rs_m.contiguous(), ss=ss))
+        return out
+
     # ------------------------------------------------------------------ forward (saves what backward needs)
     def forward(self, mod, input_frames, query_mask, queries_per_video=1):
         if not input_frames.is_cuda:
             raise RuntimeError('tcow_b200 runs on a CUDA sm_100 device only; move the module and inputs to the GPU '
                                '(there is no CPU fallback)')
-        if mod.training and float(mod.drop_path_rate) > 0.0:
-            raise NotImplementedError('tcow_b200 trains with drop_path_rate=0 (stochastic depth, vit_utils.py:139-164, '
-                                      'is not implemented; SURVEY.md §8a F.4): construct Seeker(drop_path_rate=0.0)')
         device = input_frames.device
         bbm = mod.tracker_backbone
         V, Cin, T, Hf, Wf = input_frames.shape
@@ -242,6 +279,9 @@ class SeekerTrainEngine:
             sv.blocks = []
             L, G = self._launch, self._gemm
             self.launches = 0
+            drop = self._drop_path_scales(mod, len(pk.blocks), B, N, T, M, R, Rs, use_cls, causal, device)
+            if drop is not None and not self.merge_temporal_proj:
+                raise NotImplementedError('stochastic depth needs the merged temporal projection (merge_temporal_proj=True)')
             L('patch_gather', ops.patch_gather, frames, query, sv.PM, P, bool(bbm.pretrained), queries_per_video, 0)
             L('embed_init', ops.embed_init, X, pk.patch_b, pk.pos, pk.time, pk.cls, B, N, T, D)
             G('gemm_patch', sv.PM, pk.patch_w, None, X[:M], EPI_F32_ADD)
@@ -251,14 +291,18 @@ class SeekerTrainEngine:
                 L('ln_train', ops.layernorm_train, X[:rows], params[0], params[1], a, xh, rs, nbytes=8.0 * rows * D)
                 return a, xh, rs
 
-            for w in pk.blocks:
+            for bi, w in enumerate(pk.blocks):
                 s = _Saved()
+                s.dp = dp = None if drop is None else drop[bi]
                 # ---- temporal attention + temporal_fc + residual (vit.py:169-176); cls rows untouched
                 s.A_t, s.xh_t, s.rs_t = ln_save(M, w.tn1)
                 s.QKV_t, s.O_t = e((M, 3 * D)), e((M, D))
                 G('gemm_qkv', s.A_t, w.t_qkv[0], w.t_qkv[1], s.QKV_t, EPI_BF16)
                 L('attn_temporal', ops.attn_temporal, s.QKV_t, s.O_t, B * N, T, HEADS, causal_diag)
-                if self.merge_temporal_proj:
+                if dp is not None:     # drop_path sits between proj and temporal_fc (vit.py:172-174)
+                    L('gemm_proj', ops.gemm_add_scaled, s.O_t, w.t_out[0], w.t_out[3], w.t_out[4], dp['rs_t'], dp['rs_t'],
+                      X[:M], flops=2.0 * M * D * D)
+                elif self.merge_temporal_proj:
                     G('gemm_proj', s.O_t, w.t_out[0], w.t_out[1], X[:M], EPI_F32_ADD)
                 else:
                     s.P_t = e((M, D))
@@ -272,14 +316,24 @@ class SeekerTrainEngine:
                 G('gemm_qkv', s.A_s, w.s_qkv[0], w.s_qkv[1], s.QKV_s, EPI_BF16)
                 L('attn_spatial', ops.attn_spatial_train, s.QKV_s, s.O_s, s.OCLS, s.LSE, B, N, T, HEADS, use_cls, M)
                 if use_cls and causal == 0:
-                    L('cls_merge', ops.cls_merge, s.OCLS, s.O_s, B, T, D, M, 0)
-                G('gemm_proj', s.O_s, w.s_proj[0], w.s_proj[1], X[:Rs], EPI_F32_ADD)
+                    # mean over frames of the (per-frame dropped) cls outputs (vit.py:186-195)
+                    ocls = s.OCLS if dp is None else s.OCLS * dp['ss'].view(B, T, 1)
+                    L('cls_merge', ops.cls_merge, ocls, s.O_s, B, T, D, M, 0)
+                if dp is not None:
+                    L('gemm_proj', ops.gemm_add_scaled, s.O_s, w.s_proj[0], w.s_proj[1], None, dp['rs_s'], dp['bs_s'],
+                      X[:Rs], flops=2.0 * Rs * D * D)
+                else:
+                    G('gemm_proj', s.O_s, w.s_proj[0], w.s_proj[1], X[:Rs], EPI_F32_ADD)
                 # ---- MLP on every token incl. cls (vit.py:216)
                 s.A_m, s.xh_m, s.rs_m = ln_save(R, w.n2)
                 s.Z, s.H = e((R, 4 * D)), e((R, 4 * D))
                 L('gemm_fc1', ops.gemm_aux, s.A_m, w.fc1[0], w.fc1[1], s.H, s.Z, EPI_BF16_GELU_AUX,
                   flops=2.0 * R * 4 * D * D)
-                G('gemm_fc2', s.H, w.fc2[0], w.fc2[1], X, EPI_F32_ADD)
+                if dp is not None:
+                    L('gemm_fc2', ops.gemm_add_scaled, s.H, w.fc2[0], w.fc2[1], None, dp['rs_m'], dp['rs_m'], X,
+                      flops=2.0 * R * 4 * D * D)
+                else:
+                    G('gemm_fc2', s.H, w.fc2[0], w.fc2[1], X, EPI_F32_ADD)
                 sv.blocks.append(s)
             # ---- head (vision_tf.py:152-153, mask_tracker.py:112-137)
             if mod.norm_embeddings:
@@ -309,6 +363,7 @@ class SeekerTrainEngine:
             sc = self._scratch_for(device, R, D, pk.n_pad)
             G_, Gb, dA, dO, dQKV, dZ, dLOW, ws = (sc[k] for k in ('G', 'Gb', 'dA', 'dO', 'dQKV', 'dZ', 'dLOW', 'ws'))
             lay = _GradLayout(len(pk.blocks), D, Kp, N + 1, T, pk.n_pad, merged)
+            sv.blocks_dp = [None] * len(pk.blocks)
             flat = torch.zeros(lay.total, device=device, dtype=torch.float32)
             gv = lambda name: lay.view(flat, name)
             L, G, WG = self._launch, self._gemm, self._wgrad
@@ -345,23 +400,40 @@ class SeekerTrainEngine:
             for bi in reversed(range(len(pk.blocks))):
                 w, s = pk.blocks[bi], sv.blocks[bi]
                 p = f'b{bi}.'
+                dp = s.dp
+                Gs = Gb                 # branch gradient = residual gradient, row-scaled under stochastic depth
+
+                def scaled(rows, scale):
+                    L('scale_rows', ops.scale_rows, Gb[:rows], scale, sc['Gs'][:rows], nbytes=4.0 * rows * D)
+                    return sc['Gs']
                 # ---- MLP (vit.py:216)
-                colsum(Gb, p + 'fc2_b')
-                WG('wgrad_fc2', Gb, s.H, gv(p + 'fc2_w'))
-                L('dgrad_fc2', ops.gemm_aux, Gb, w.fc2[2], None, dZ, s.Z, EPI_BF16_DGELU, flops=2.0 * R * 4 * D * D)
+                if dp is not None:
+                    Gs = scaled(R, dp['rs_m'])
+                colsum(Gs, p + 'fc2_b')
+                WG('wgrad_fc2', Gs, s.H, gv(p + 'fc2_w'))
+                L('dgrad_fc2', ops.gemm_aux, Gs, w.fc2[2], None, dZ, s.Z, EPI_BF16_DGELU, flops=2.0 * R * 4 * D * D)
                 colsum(dZ, p + 'fc1_b')
                 WG('wgrad_fc1', dZ, s.A_m, gv(p + 'fc1_w'))
                 G('dgrad_fc1', dZ, w.fc1[2], None, dA, EPI_BF16)
                 ln_bwd(R, s.xh_m, s.rs_m, w.n2[0], p + 'n2_g', p + 'n2_b')
                 # ---- spatial attention (vit.py:179-215)
-                colsum(Gb[:Rs], p + 's_proj_b')
-                WG('wgrad_proj', Gb[:Rs], s.O_s, gv(p + 's_proj_w'))
-                G('dgrad_proj', Gb[:Rs], w.s_proj[2], None, dO[:Rs], EPI_BF16)
+                Gs = Gb
+                if dp is not None:
+                    Gs = scaled(Rs, dp['rs_s'])
+                    colsum(Gs[:M], p + 's_proj_b')
+                    if use_cls:      # cls rows: the bias term carries its own scale (mean of the frame scales, causal==0)
+                        gv(p + 's_proj_b').add_((dp['bs_s'][M:R, None] * Gb[M:R].float()).sum(0))
+                else:
+                    colsum(Gs[:Rs], p + 's_proj_b')
+                WG('wgrad_proj', Gs[:Rs], s.O_s, gv(p + 's_proj_w'))
+                G('dgrad_proj', Gs[:Rs], w.s_proj[2], None, dO[:Rs], EPI_BF16)
                 dOCLS = dCLS = None
                 if use_cls:
                     dOCLS = torch.empty((B, T, D), device=device, dtype=torch.float32)
                     dCLS = torch.empty((B, T, 3, D), device=device, dtype=torch.float32)
                     L('cls_merge_bwd', ops.cls_merge_bwd, dO, dOCLS, B, T, D, M, 0 if causal == 0 else 1)
+                    if dp is not None and causal == 0:
+                        dOCLS.mul_(dp['ss'].view(B, T, 1))
                 S = N + (1 if use_cls else 0)
                 L('attn_spatial_bwd', ops.attn_spatial_bwd, s.QKV_s, s.O_s, s.OCLS, dO, dOCLS, s.LSE, dQKV, dCLS, B, N, T,
                   HEADS, use_cls, M, flops=10.0 * B * T * HEADS * S * S * 64, nbytes=16.0 * M * D)
@@ -371,9 +443,13 @@ class SeekerTrainEngine:
                 ln_bwd(Rs, s.xh_s, s.rs_s, w.n1[0], p + 'n1_g', p + 'n1_b')
                 # ---- temporal attention + temporal_fc (vit.py:169-176)
                 if merged:
-                    colsum(Gb[:M], p + 't_out_b')
-                    WG('wgrad_proj', Gb[:M], s.O_t, gv(p + 't_out_w'))
-                    G('dgrad_proj', Gb[:M], w.t_out[2], None, dO[:M], EPI_BF16)
+                    Gs = Gb
+                    if dp is not None:
+                        Gs = scaled(M, dp['rs_t'])
+                        colsum(Gb[:M], p + 't_out_b2')          # temporal_fc.bias sits outside DropPath
+                    colsum(Gs[:M], p + 't_out_b')
+                    WG('wgrad_proj', Gs[:M], s.O_t, gv(p + 't_out_w'))
+                    G('dgrad_proj', Gs[:M], w.t_out[2], None, dO[:M], EPI_BF16)
                 else:
                     colsum(Gb[:M], p + 't_fc_b')
                     WG('wgrad_proj', Gb[:M], s.P_t, gv(p + 't_fc_w'))
@@ -387,6 +463,7 @@ class SeekerTrainEngine:
                 WG('wgrad_qkv', dQKV[:M], s.A_t, gv(p + 't_qkv_w'))
                 G('dgrad_qkv', dQKV[:M], w.t_qkv[2], None, dA[:M], EPI_BF16)
                 ln_bwd(M, s.xh_t, s.rs_t, w.tn1[0], p + 'tn1_g', p + 'tn1_b')
+                sv.blocks_dp[bi] = s
                 sv.blocks[bi] = None           # this block's activations are no longer needed
                 if sync is not None:
                     sync.ready(*lay.block_ranges[len(pk.blocks) - 1 - bi])
@@ -398,10 +475,11 @@ class SeekerTrainEngine:
                 sync.ready(*lay.embed_range)
                 sync.finish()
             self.last_flat = flat
-            return self._unpack(mod, pk, lay, flat, merged)
+            dropped = [b is not None and b.dp is not None for b in sv.blocks_dp]
+            return self._unpack(mod, pk, lay, flat, merged, dropped)
 
     # ------------------------------------------------------------------ packed gradients -> reference parameters
-    def _unpack(self, mod, pk, lay, flat, merged):
+    def _unpack(self, mod, pk, lay, flat, merged, dropped=None):
         gv = lambda name: lay.view(flat, name)
         D = gv('norm_g').shape[0]
         g = {}
@@ -421,10 +499,12 @@ class SeekerTrainEngine:
                 g[q + theirs + '.weight'], g[q + theirs + '.bias'] = gv(p + ours + '_w'), gv(p + ours + '_b')
             if merged:
                 # W_m = Wf Wp, b_m = Wf bp + bf  =>  dWf = dW_m Wp^T + db_m bp^T, dWp = Wf^T dW_m, dbp = Wf^T db_m, dbf = db_m
+                # (under stochastic depth the Wf bp part of the bias is inside DropPath, bf outside: two bias gradients)
                 Wp, bp, Wf, _ = w.raw_t
                 dWm, dbm = gv(p + 't_out_w'), gv(p + 't_out_b')
+                dbf = gv(p + 't_out_b2') if (dropped is not None and dropped[i]) else dbm
                 g[q + 'temporal_fc.weight'] = _mm(dWm, Wp.t()) + dbm[:, None] * bp[None, :]
-                g[q + 'temporal_fc.bias'] = dbm
+                g[q + 'temporal_fc.bias'] = dbf
                 g[q + 'temporal_attn.proj.weight'] = _mm(Wf.t(), dWm)
                 g[q + 'temporal_attn.proj.bias'] = _mm(Wf.t(), dbm[:, None])[:, 0]
             else:

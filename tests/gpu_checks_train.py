@@ -72,6 +72,34 @@ def check_gemm_dgelu(M, N, K):
     return bad, 2.0 ** -8 * ref.abs().max().item() + 1e-3, f'gemm_dgelu M={M} N={N} K={K}'
 
 
+def check_gemm_add_scaled(M, N, K, bias2=True):
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(21)
+    a = (torch.randn(M, K, device=d, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=d, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=d, generator=g) * 0.1
+    b2 = torch.randn(N, device=d, generator=g) * 0.1 if bias2 else None
+    rs = (torch.rand(M, device=d, generator=g) > 0.4).float() / 0.6
+    bs = torch.rand(M, device=d, generator=g)
+    x0 = torch.randn(M, N, device=d, generator=g)
+    x = x0.clone()
+    ops.gemm_add_scaled(a, w, bias, b2, rs, bs, x)
+    torch.cuda.synchronize()
+    ref = x0 + rs[:, None] * (a.float() @ w.float().t()) + bs[:, None] * bias + (b2 if bias2 else 0)
+    return (x - ref).abs().max().item(), 3e-4 * max(1.0, (K / 768) ** 0.5), f'gemm_add_scaled M={M} N={N} K={K} bias2={bias2}'
+
+
+def check_scale_rows(rows, N):
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(22)
+    x = torch.randn(rows, N, device=d, generator=g).to(torch.bfloat16)
+    sc = (torch.rand(rows, device=d, generator=g) > 0.5).float() * 2
+    out = torch.empty_like(x)
+    ops.scale_rows(x, sc, out)
+    torch.cuda.synchronize()
+    return (out.float() - (x.float() * sc[:, None]).to(torch.bfloat16).float()).abs().max().item(), 0.0, f'scale_rows {rows}x{N}'
+
+
 def check_ln_train_bwd(rows, D=768, accumulate=True):
     d = _dev()
     g = torch.Generator(device=d).manual_seed(14)
@@ -247,6 +275,10 @@ TRAIN_CHECKS = [
     ('gemm_gelu_aux_small', lambda: check_gemm_gelu_aux(100, 128, 64)),
     ('gemm_dgelu', lambda: check_gemm_dgelu(9001, 3072, 768)),
     ('gemm_dgelu_small', lambda: check_gemm_dgelu(77, 64, 128)),
+    ('gemm_add_scaled_proj', lambda: check_gemm_add_scaled(9008, 768, 768)),
+    ('gemm_add_scaled_fc2', lambda: check_gemm_add_scaled(9001, 768, 3072, bias2=False)),
+    ('gemm_add_scaled_small', lambda: check_gemm_add_scaled(100, 128, 64)),
+    ('scale_rows', lambda: check_scale_rows(9001, 768)),
     ('ln_train_bwd', lambda: check_ln_train_bwd(9001)),
     ('ln_train_bwd_noacc', lambda: check_ln_train_bwd(300, accumulate=False)),
     ('ln_train_bwd_1024', lambda: check_ln_train_bwd(100, 1024)),

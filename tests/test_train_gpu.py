@@ -10,7 +10,7 @@ import torch
 
 from conftest import cached_state_dict
 from oracle import make_golden_grads as mgg
-from test_train_host import GRAD_CASES, check_against_fixture, load_grad_golden
+from test_train_host import GRAD_CASES, check_against_fixture, load_drop_path, load_grad_golden
 
 import tcow_b200
 from tcow_b200 import synth
@@ -72,12 +72,14 @@ def our_grads(net, rgb, q, tm, tf):
 def test_backward_matches_oracle_autograd_and_reference_fixture(name, logger):
     meta, norms, samples, projs = load_grad_golden(name)
     net = build(logger, meta)
+    dp = load_drop_path(name, meta)          # the Bernoulli draws the reference made (stochastic-depth fixtures)
+    net.seeker.train_engine().drop_path_override = dp
     rgb, q, tm, tf = case_data(meta)
     loss, grads, _ = our_grads(net, rgb, q, tm, tf)
     assert all(g is not None for g in grads.values())
     assert abs(loss - meta['loss']) < 5e-3
     sd = cached_state_dict(meta['weight_seed'], meta['T'], meta['Hf'], meta['Wf'])
-    _, ref = mgg.oracle_grads(sd, meta, rgb, q, tm, tf)
+    _, ref = mgg.oracle_grads(sd, meta, rgb, q, tm, tf, dp)
     bad, wc, wr = compare(grads, ref)
     assert not bad, f'{len(bad)} tensors out of tolerance (worst cos {wc:.5f}, rel {wr:.4f}): {bad[:8]}'
     # and against what the reference itself produced (norms, sampled entries, projections per tensor)
@@ -152,12 +154,24 @@ def test_optimizer_step_reduces_loss_and_repacks_weights(logger):
     assert losses[-1] < losses[0] - 1e-3, losses
 
 
-def test_training_rejects_what_it_does_not_implement(logger):
+def test_stochastic_depth_draws(logger):
+    """train() with drop_path_rate > 0 draws its own masks: outputs vary between calls with the expected frequency
+    structure (block 0 never drops); eval() is deterministic and equals the drop-free forward."""
     meta, *_ = load_grad_golden('grad_small_causal1')
-    net = build(logger, meta, drop_path_rate=0.1)
+    net = build(logger, meta, drop_path_rate=0.5)
     rgb, q, tm, tf = case_data(meta)
-    with pytest.raises(NotImplementedError, match='drop_path'):
-        net(rgb.to(DEV), q.to(DEV))
-    net.eval()                                        # eval mode: DropPath is the identity, gradients are fine
-    mask, _ = net(rgb.to(DEV), q.to(DEV))
-    assert mask.requires_grad
+    torch.manual_seed(3)
+    a, _ = net(rgb.to(DEV), q.to(DEV))
+    b, _ = net(rgb.to(DEV), q.to(DEV))
+    assert a.requires_grad and (a - b).abs().max().item() > 1e-3
+    net.eval()
+    c, _ = net(rgb.to(DEV), q.to(DEV))
+    d, _ = net(rgb.to(DEV), q.to(DEV))
+    assert torch.equal(c, d)
+    with torch.no_grad():
+        e, _ = net(rgb.to(DEV), q.to(DEV))
+    assert (c - e).abs().max().item() <= 2e-3
+    scales = net.seeker.train_engine()._drop_path_scales(net.seeker.train(), 12, 2, 6, 4, 48, 50, 50, True, 1, torch.device(DEV))
+    assert scales[0] is None and all(s is not None for s in scales[1:])
+    last = scales[-1]['rs_t']
+    assert set(last.unique().tolist()) <= {0.0, 2.0}          # keep = 0.5 in the last block: survivors scaled by 2

@@ -25,6 +25,18 @@ def load_grad_golden(name):
     return meta, z['norms'], z['samples'], z['projs']
 
 
+def load_drop_path(name, meta):
+    """The stochastic-depth keep masks the reference drew for this fixture (None when DropPath was off)."""
+    if 'drop_keep' not in meta:
+        return None
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    out = []
+    for i, keep in enumerate(meta['drop_keep']):
+        out.append(None if keep is None else
+                   dict(keep=keep, **{w: torch.from_numpy(z[f'dp{i}_{w}'].astype(np.float32)) for w in 'tsm'}))
+    return out
+
+
 def check_against_fixture(grads, meta, norms, samples, projs, rel_tol, abs_floor=1e-9):
     """grads: {full reference parameter name: tensor}.  Returns the worst normalised deviation (<= 1 passes)."""
     worst = (0.0, '')
@@ -39,14 +51,14 @@ def check_against_fixture(grads, meta, norms, samples, projs, rel_tol, abs_floor
     return worst
 
 
-@pytest.mark.parametrize('name', GRAD_CASES[:2])
+@pytest.mark.parametrize('name', ['grad_small_causal1', 'grad_small_causal0', 'grad_small_droppath1'])
 def test_oracle_autograd_matches_reference_gradients(name):
     meta, norms, samples, projs = load_grad_golden(name)
     T, Hf, Wf = meta['T'], meta['Hf'], meta['Wf']
     sd = cached_state_dict(meta['weight_seed'], T, Hf, Wf, meta.get('flag_channels', 3))
     rgb, q = synth.make_batch(meta['samples'], num_frames=T, frame_height=Hf, frame_width=Wf)
     tm, tf = synth.make_targets(meta['samples'], num_frames=T, frame_height=Hf, frame_width=Wf)
-    loss, grads = mgg.oracle_grads(sd, meta, rgb, q, tm, tf)
+    loss, grads = mgg.oracle_grads(sd, meta, rgb, q, tm, tf, load_drop_path(name, meta))
     assert abs(loss - meta['loss']) < 1e-5
     dev, where = check_against_fixture(grads, meta, norms, samples, projs, rel_tol=1e-3)
     assert dev <= 1.0, f'oracle autograd deviates from the reference fixture at {where}: {dev:.3f} x tolerance'
@@ -65,7 +77,8 @@ def test_grad_layout_is_disjoint_aligned_and_ordered():
     assert lay.slots['b11.fc2_w'][0] == lay.block_ranges[0][0]
     n_params = sum(int(np.prod(s)) for _, s in lay.slots.values())
     # merged temporal projection: one 768x768 (+bias) per block instead of two; pooled head 64x768 instead of 771x768
-    assert n_params == 122145027 - 12 * (768 * 768 + 768) - (771 * 768 + 771) + (64 * 768 + 64) - 768 - 768
+    # (+ a second 768-bias slot per block for the part of the merged bias that sits outside DropPath)
+    assert n_params == 122145027 - 12 * (768 * 768 + 768) + 12 * 768 - (771 * 768 + 771) + (64 * 768 + 64) - 768 - 768
 
 
 def _sync_worker(rank, world, port, q):
