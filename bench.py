@@ -300,6 +300,124 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """--workload train (BASELINE configs[3]): fwd + bwd + AdamW step, 2 videos x 3 queries per GPU, data-parallel with
+    the bucketed gradient all-reduce of tcow_b200/ddp.py overlapped with the backward (NCCL over NVLink)."""
+    import torch
+    import torch.distributed as dist
+
+    import tcow_b200
+    from tcow_b200 import ddp, synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    peaks = load_peaks()
+    kw = dict(SEEKER_KW)
+    kw['drop_path_rate'] = args.drop_path
+    net = tcow_b200.Seeker(logging.getLogger('bench'), **kw)
+    net.load_state_dict(synth.make_state_dict(901, num_frames=T, frame_height=HF, frame_width=WF))
+    net = net.to(dev).train()
+    ddp.broadcast_parameters(net)
+    sync = ddp.attach(net) if world > 1 else None
+    if sync is not None:
+        sync.timing = True
+    eng = net.seeker.train_engine()
+    V, Q = args.videos, 3
+    B = V * Q
+    g = torch.Generator().manual_seed(77 + rank)
+    rgb_h = torch.rand(V, 3, T, HF, WF, generator=g).pin_memory()
+    q_h = torch.stack([torch.stack([synth.make_clip(1000 + rank * B + v * Q + j, T, HF, WF)[1] for j in range(Q)])
+                       for v in range(V)]).pin_memory()
+    tm, tf = synth.make_targets(list(range(rank * B, rank * B + B)), T, HF, WF)
+    tm, tf = tm.to(dev), tf.to(dev)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, fused=True)       # args.py:108,179 defaults
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        rgb, q = rgb_h.to(dev, non_blocking=True), q_h.to(dev, non_blocking=True)   # inputs start on the host every step
+        opt.zero_grad(set_to_none=True)
+        mask, flags = net.forward_queries(rgb, q)
+        loss = synth.training_loss(mask.flatten(0, 1), flags.flatten(0, 1), tm, tf)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    exposed = []
+    launches = 0
+    for _ in range(args.steps):
+        loss = step()
+        launches += eng.launches
+        if sync is not None:
+            exposed.append(sync.exposed_time_ms())
+    e1.record()
+    loss_val = float(loss.detach())       # the step's result read back to the host
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel-class breakdown of one more (untimed) step
+    eng.profile = []
+    step()
+    torch.cuda.synchronize()
+    prof, eng.profile = eng.profile, None
+    if rank == 0:
+        agg = {}
+        for kind, flops, nbytes, a, b in prof:
+            d = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b); d[1] += flops; d[2] += nbytes; d[3] += 1
+        breakdown = {k: {'ms_per_step': round(v[0], 3), 'launches_per_step': v[3],
+                         'tflops': round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] and v[0] else None,
+                         'gbs': round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[2] and v[0] else None}
+                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        gemm = [v for k, v in agg.items() if k.startswith(('gemm', 'dgrad', 'wgrad'))]
+        gemm_ms, gemm_fl = sum(v[0] for v in gemm), sum(v[1] for v in gemm)
+        ms_step = ms / args.steps
+        value = world * B * args.steps / (ms * 1e-3)
+        line = {'metric': 'seeker_train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'config': {'workload': f'TCOW Seeker training step (fwd + hand-written bwd + fused AdamW), T=30 240x320, causal, '
+                                       f'{V} videos x {Q} queries per GPU, drop_path_rate={args.drop_path}, data-parallel x{world} '
+                                       f'with bucketed NCCL gradient all-reduce overlapped with the backward (BASELINE configs[3])',
+                           'batch_per_gpu': B, 'parallelism': f'dp{world}',
+                           'l2': 'activation working set >> 126 MB L2; no flush needed'},
+                'roofline': {'bound': 'tensor', 'achieved': round(gemm_fl / (gemm_ms * 1e-3) / 1e12, 1) if gemm_ms else None,
+                             'peak': peaks['sustained'], 'unit': 'TFLOP/s',
+                             'frac': round(gemm_fl / (gemm_ms * 1e-3) / 1e12 / peaks['sustained'], 4) if gemm_ms else None,
+                             'traffic': None, 'kernel': 'gemm_bf16_tn_kernel + gemm_bf16_wgrad_kernel (tcgen05), all launches of a step',
+                             'step_tflops_algorithmic': round(3 * FLOP_PER_CLIP * B / (ms_step * 1e-3) / 1e12, 1),
+                             'step_frac_of_burst_peak': round(3 * FLOP_PER_CLIP * B / (ms_step * 1e-3) / 1e12 / peaks['burst'], 4)},
+                'allreduce': {'bytes_per_step': int(eng.last_flat.numel() * 4) if eng.last_flat is not None else None,
+                              'exposed_ms_per_step': round(statistics.mean(x for x in exposed if x is not None), 3) if exposed and exposed[0] is not None else 0.0},
+                'breakdown': breakdown, 'clocks': clocks, 'loss': loss_val,
+                'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': int(rgb_h.numel() * 4 + q_h.numel() * 4),
+                        'd2h_bytes_per_step': 4, 'note': 'inputs are uploaded from pinned host memory inside every timed step'},
+                'gpu_launches': launches}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -309,10 +427,16 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunk', type=int, default=0, help='clips per engine pass (0 = engine default)')
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train'],
+                    help='infer = BASELINE configs[1] (the headline metric, default); train = configs[3] (fwd+bwd+AdamW, DDP)')
+    ap.add_argument('--videos', type=int, default=2, help='train: videos per GPU (x3 queries each)')
+    ap.add_argument('--drop-path', type=float, default=0.1, help='train: stochastic-depth rate (args.py default 0.1)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'train':
+        run_train(args)
     else:
         run_ours(args)
 
