@@ -418,6 +418,75 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_sweep_bench(args):
+    """--workload sweep (BASELINE configs[2]): eval/test.py-style inference sweep — V synthetic 200-frame videos x 4 queries
+    x the temporal strides that fit (6) — sharded by clip over the ranks, no collective on the data path (strong
+    scaling: the sweep is fixed, time = max over ranks, host clip assembly + upload + metrics read-back included)."""
+    import torch
+    import torch.distributed as dist
+
+    import tcow_b200
+    from tcow_b200 import sweep, synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    net = tcow_b200.Seeker(logging.getLogger('bench'), **SEEKER_KW)
+    net.load_state_dict(synth.make_state_dict(901, num_frames=T, frame_height=HF, frame_width=WF))
+    net = net.to(dev).eval()
+    V, Q, F = args.videos_total, 4, 200
+    items = sweep.plan_sweep(V, Q, F, T, query_idx=15)
+    mine = sweep.shard_clips(items, rank, world)
+    my_videos = sorted({it.video for it in mine})
+    g = torch.Generator().manual_seed(5)
+    base = torch.rand(3, F, HF, WF, generator=g)                 # one synthetic video, rolled per video id
+    videos = {v: torch.roll(base, shifts=7 * v, dims=3).pin_memory() for v in my_videos}
+    tgt = (torch.rand(3, F, HF // 8, WF // 8, generator=g) > 0.6).float().repeat_interleave(8, 2).repeat_interleave(8, 3)
+
+    def get_query(v, q):
+        m = torch.zeros(HF, WF)
+        m[20 + 30 * q:60 + 30 * q, 40 + 50 * q:100 + 50 * q] = 1
+        return m
+
+    fn = lambda its: sweep.run_sweep(net, its, videos.__getitem__, get_query, lambda v, q: tgt, T, dev, clips_per_pass=2)
+    fn(mine[:8])                                                   # warm-up (weights packed, graphs captured)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = fn(mine)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    merged = sweep.gather_to_rank0({k: v for k, v in res.items()})
+    if rank == 0:
+        assert len(merged) == len(items)
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        sweep.write_itemized_csv(os.path.join(ROOT, 'gpurun_out', f'itemized_results_{world}gpu.csv'), merged)
+        line = {'metric': 'seeker_sweep_samples_per_s', 'value': len(items) / dt, 'unit': 'samples/s', 'n_gpus': world,
+                'steps': 1, 'warmup': 1, 'ms_per_step': 1e3 * dt, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'config': {'workload': f'eval/test.py-style sweep: {V} videos (200 frames, 240x320) x {Q} queries x 6 strides = '
+                                       f'{len(items)} samples, sharded by clip over {world} GPU(s), no collective (BASELINE configs[2]); '
+                                       f'host clip assembly, upload and IoU read-back inside the timed region',
+                           'parallelism': f'clip-sharded x{world}'},
+                'e2e': {'value': len(items) / dt, 'unit': 'samples/s',
+                        # every video (and its target masks) is uploaded once; clips are gathered on the device
+                        'h2d_bytes_per_step': int(V * 2 * 3 * F * HF * WF * 4 + len(items) * HF * WF * 4),
+                        'd2h_bytes_per_step': int(len(items) * (3 * T * 3 + 3) * 4)},
+                'gpu_launches': net.seeker.engine().launches * (len(mine) // (2 * Q))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -427,8 +496,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunk', type=int, default=0, help='clips per engine pass (0 = engine default)')
-    ap.add_argument('--workload', default='infer', choices=['infer', 'train'],
-                    help='infer = BASELINE configs[1] (the headline metric, default); train = configs[3] (fwd+bwd+AdamW, DDP)')
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'sweep'],
+                    help='infer = BASELINE configs[1] (the headline metric, default); train = configs[3] (fwd+bwd+AdamW, DDP); '
+                         'sweep = configs[2] (clip-sharded evaluation sweep)')
+    ap.add_argument('--videos-total', type=int, default=8, help='sweep: videos in the whole sweep (fixed as GPUs grow)')
     ap.add_argument('--videos', type=int, default=2, help='train: videos per GPU (x3 queries each)')
     ap.add_argument('--drop-path', type=float, default=0.1, help='train: stochastic-depth rate (args.py default 0.1)')
     args = ap.parse_args()
@@ -437,6 +508,8 @@ def main():
         run_reference(args)
     elif args.workload == 'train':
         run_train(args)
+    elif args.workload == 'sweep':
+        run_sweep_bench(args)
     else:
         run_ours(args)
 

@@ -124,6 +124,11 @@ int tcow_mask_upsample(const float* low, int64_t ld_low, float* out, int B, int 
 int tcow_flag_mean(const float* low, int64_t ld_low, float* flags, int B, int N, int T, int F, int col0,
                    void* stream);
 
+/* Mask areas behind the IoU metrics (eval/metrics.py:18-41; the reference builds three boolean tensors and sums each):
+ * for every one of `images` = B*C*T images of hw = Hf*Wf pixels (logits and target contiguous, same layout),
+ * areas[img] = (|target > 0.5|, |logit > 0 & target > 0.5|, |logit > 0 or target > 0.5|) as fp32. */
+int tcow_mask_iou_areas(const float* logits, const float* target, float* areas, int images, int hw, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training step (BASELINE configs[3]: fwd+bwd, data-parallel).  The reference gets its backward from torch.autograd
  * over the modules cited above (train.py:93-101 loss.backward(); optimizer.step()); these entry points are the

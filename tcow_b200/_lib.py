@@ -36,6 +36,7 @@ SIGNATURES = {
     'tcow_mask_upsample': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                            c_void_p],
     'tcow_flag_mean': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'tcow_mask_iou_areas': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     # ---- training step
     'tcow_gemm_bf16_aux': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                            c_int, c_int, c_int, c_int, c_void_p],

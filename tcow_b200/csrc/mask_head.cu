@@ -80,7 +80,50 @@ __global__ void __launch_bounds__(128) flag_mean_kernel(const float* __restrict_
   }
 }
 
+// Per-image mask areas for the IoU metrics (eval/metrics.py:18-41): with pred = logit > 0 and gt = target > 0.5,
+// areas[img] = (|gt|, |pred & gt|, |pred | gt|); one CTA per (b, c, t) image, one pass over logits and targets.
+__global__ void __launch_bounds__(256) mask_iou_areas_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                             float* __restrict__ areas, int hw) {
+  const int img = blockIdx.x;
+  const float4* l4 = reinterpret_cast<const float4*>(logits + static_cast<int64_t>(img) * hw);
+  const float4* t4 = reinterpret_cast<const float4*>(target + static_cast<int64_t>(img) * hw);
+  int gt = 0, inter = 0, uni = 0;
+  for (int i = threadIdx.x; i < hw / 4; i += blockDim.x) {
+    const float4 l = __ldcs(l4 + i), t = __ldcs(t4 + i);
+    const float lv[4] = {l.x, l.y, l.z, l.w}, tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool p = lv[e] > 0.f, g = tv[e] > 0.5f;
+      gt += g; inter += (p && g); uni += (p || g);
+    }
+  }
+  __shared__ int s_red[3][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gt += __shfl_xor_sync(0xffffffffu, gt, o);
+    inter += __shfl_xor_sync(0xffffffffu, inter, o);
+    uni += __shfl_xor_sync(0xffffffffu, uni, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_red[0][threadIdx.x >> 5] = gt; s_red[1][threadIdx.x >> 5] = inter; s_red[2][threadIdx.x >> 5] = uni;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int s = 0;
+    for (int w = 0; w < 8; ++w) s += s_red[threadIdx.x][w];
+    areas[static_cast<int64_t>(img) * 3 + threadIdx.x] = static_cast<float>(s);
+  }
+}
+
 }  // namespace tcow
+
+extern "C" int tcow_mask_iou_areas(const float* logits, const float* target, float* areas, int images, int hw,
+                                   void* stream) {
+  using namespace tcow;
+  if (!logits || !target || !areas || images <= 0 || hw <= 0 || (hw % 4)) return set_error(TCOW_ERR_ARG, "mask_iou_areas: bad argument");
+  mask_iou_areas_kernel<<<images, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, target, areas, hw);
+  return check_launch("mask_iou_areas_kernel");
+}
 
 extern "C" int tcow_mask_upsample(const float* low, int64_t ld_low, float* out, int B, int T, int Ho, int Wo, int C,
                                   int pp, int stride, int mode, void* stream) {

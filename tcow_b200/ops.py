@@ -261,3 +261,16 @@ def scale_rows(x, scale, out):
     _lib.call('tcow_scale_rows_bf16', x.data_ptr(), x.stride(0), scale.data_ptr(), out.data_ptr(), out.stride(0), rows, N,
               _stream())
     return out
+
+
+def mask_iou_areas(logits, target):
+    """(..., Hf, Wf) fp32 logits and targets -> (..., 3) fp32: |gt|, |pred & gt|, |pred | gt| per image
+    (pred = logit > 0, gt = target > 0.5; eval/metrics.py:18-41)."""
+    _chk(logits, torch.float32, 'mask_iou_areas.logits'); _chk(target, torch.float32, 'mask_iou_areas.target')
+    if logits.shape != target.shape or not (logits.is_contiguous() and target.is_contiguous()):
+        raise ValueError('mask_iou_areas: logits and target must be contiguous and of equal shape')
+    hw = logits.shape[-1] * logits.shape[-2]
+    images = logits.numel() // hw
+    out = torch.empty(*logits.shape[:-2], 3, device=logits.device, dtype=torch.float32)
+    _lib.call('tcow_mask_iou_areas', logits.data_ptr(), target.data_ptr(), out.data_ptr(), images, hw, _stream())
+    return out

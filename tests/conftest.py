@@ -35,7 +35,7 @@ def load_golden(name):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith('grad_'))
 
 
 @pytest.fixture(scope='session')

@@ -15,6 +15,9 @@ TOL_LOGIT = 1e-2
 TOL_IOU = 0.99
 
 
+DEV = 'cuda:0'
+
+
 def build(logger, meta, **over):
     T, Hf, Wf = meta['T'], meta['Hf'], meta['Wf']
     fc = meta.get('flag_channels', 3)
@@ -200,5 +203,42 @@ def test_errors_match_reference_types(logger):
             net(rgb[:, :, :3].cuda(), q[:, :, :3].cuda())           # vision_tf.py:96  assert T == self.T
         with pytest.raises(AssertionError):
             net(rgb.cuda(), torch.cat([q, q], 1).cuda())            # mask_tracker.py:105
-    with pytest.raises(NotImplementedError):
-        net(rgb.cuda(), q.cuda())                                   # grad mode: forward-only in round 1
+    mask, flags = net(rgb.cuda(), q.cuda())                         # grad mode: the training path (train_engine.py)
+    assert mask.requires_grad and flags.requires_grad
+    with pytest.raises(RuntimeError, match='inference plan'):       # the inference engine itself refuses gradient mode
+        net.seeker.engine().forward(net.seeker, rgb.cuda(), q.cuda())
+
+
+def test_sweep_runner_matches_per_item_forwards(logger):
+    """The clip-grouped sweep (forward_queries + on-device IoU areas) gives, per item, what a plain per-sample forward and
+    the torch restatement of eval/metrics.py:18-41 give."""
+    from tcow_b200 import ops, sweep
+    T, Hf, Wf, F = 4, 32, 48, 12
+    net = build(logger, dict(T=T, Hf=Hf, Wf=Wf, causal=1, weight_seed=901))
+    items = sweep.plan_sweep(num_videos=2, num_queries=3, num_video_frames=F, num_frames=T, query_idx=1)
+    assert len(items) == 2 * 3 * 3
+    g = torch.Generator().manual_seed(3)
+    vids = {v: torch.rand(3, F, Hf, Wf, generator=g) for v in range(2)}
+    tgt = (torch.rand(3, F, Hf, Wf, generator=g) > 0.5).float()
+
+    def get_query(v, q):
+        m = torch.zeros(Hf, Wf)
+        m[4 * q:4 * q + 8, 6 * q:6 * q + 10] = 1
+        return m
+
+    res = sweep.run_sweep(net, items, vids.__getitem__, get_query, lambda v, q: tgt, T, torch.device(DEV), clips_per_pass=2)
+    assert sorted(res) == sorted((i.video, i.query, i.frame_start, i.frame_stride) for i in items)
+    it = items[7]
+    idx = torch.arange(T) * it.frame_stride + it.frame_start
+    q = torch.zeros(1, 1, T, Hf, Wf)
+    q[0, 0, 0] = get_query(it.video, it.query)
+    with torch.no_grad():
+        mask, flags = net(vids[it.video][:, idx][None].to(DEV), q.to(DEV))
+    pred, gt = (mask[0] > 0).cpu(), tgt[:, idx] > 0.5
+    iou = (pred & gt).sum((-1, -2)).float() / ((pred | gt).sum((-1, -2)).float() + 1e-7)
+    row = res[(it.video, it.query, it.frame_start, it.frame_stride)]
+    assert abs(row['mean_snitch_iou'] - iou[0].mean().item()) < 2e-2      # a few boundary pixels may flip (bf16)
+    assert row['count_snitch_iou'] == T
+    a = ops.mask_iou_areas(mask.contiguous(), tgt[:, idx][None].to(DEV).contiguous()).cpu()[0]
+    assert torch.equal(a[..., 0], gt.sum((-1, -2)).float()) and torch.equal(a[..., 1], (pred & gt).sum((-1, -2)).float())
+    assert torch.equal(a[..., 2], (pred | gt).sum((-1, -2)).float())

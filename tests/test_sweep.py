@@ -28,6 +28,27 @@ def test_shard_partitions_everything_once():
     assert [len(b) for b in sweep.batches(items[:10], 4)] == [4, 4, 2]
 
 
+def test_shard_clips_keeps_queries_together():
+    items = sweep.plan_sweep(num_videos=3, num_queries=4, num_video_frames=200, num_frames=30, query_idx=15)
+    for world in (1, 2, 4, 8):
+        parts = [sweep.shard_clips(items, r, world) for r in range(world)]
+        assert sorted(sum(parts, []), key=items.index) == items
+        for part in parts:                       # every clip of a part carries all 4 of its queries
+            for _, its in sweep.group_by_clip(part):
+                assert [i.query for i in its] == [0, 1, 2, 3]
+
+
+def test_itemized_csv_round_trip(tmp_path):
+    rows = {(0, 1, 15, 2): dict(video=0, query=1, frame_start=15, frame_stride=2, mean_snitch_iou=0.5, count_snitch_iou=30),
+            (0, 0, 15, 1): dict(video=0, query=0, frame_start=15, frame_stride=1, mean_snitch_iou=0.25, count_snitch_iou=7)}
+    p = tmp_path / 'itemized_results.csv'
+    sweep.write_itemized_csv(str(p), rows)
+    import pandas as pd
+    df = pd.read_csv(p)
+    assert list(df.columns) == sweep.CSV_COLUMNS and len(df) == 2
+    assert df.iloc[0]['query'] == 0 and abs(df.iloc[1]['mean_snitch_iou'] - 0.5) < 1e-9
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
