@@ -443,9 +443,11 @@ def run_sweep_bench(args):
     mine = sweep.shard_clips(items, rank, world)
     my_videos = sorted({it.video for it in mine})
     g = torch.Generator().manual_seed(5)
-    base = torch.rand(3, F, HF, WF, generator=g)                 # one synthetic video, rolled per video id
+    # decoded uint8 frames and uint8 target masks in pinned host memory, as a video loader would leave them
+    base = torch.randint(0, 256, (3, F, HF, WF), generator=g, dtype=torch.uint8)   # one synthetic video, rolled per id
     videos = {v: torch.roll(base, shifts=7 * v, dims=3).pin_memory() for v in my_videos}
-    tgt = (torch.rand(3, F, HF // 8, WF // 8, generator=g) > 0.6).float().repeat_interleave(8, 2).repeat_interleave(8, 3)
+    tgt = (torch.rand(3, F, HF // 8, WF // 8, generator=g) > 0.6).to(torch.uint8).repeat_interleave(8, 2) \
+        .repeat_interleave(8, 3).pin_memory()
 
     def get_query(v, q):
         m = torch.zeros(HF, WF)
@@ -479,7 +481,7 @@ def run_sweep_bench(args):
                            'parallelism': f'clip-sharded x{world}'},
                 'e2e': {'value': len(items) / dt, 'unit': 'samples/s',
                         # every video (and its target masks) is uploaded once; clips are gathered on the device
-                        'h2d_bytes_per_step': int(V * 2 * 3 * F * HF * WF * 4 + len(items) * HF * WF * 4),
+                        'h2d_bytes_per_step': int(V * (1 + Q) * 3 * F * HF * WF + len(items) * HF * WF * 4),
                         'd2h_bytes_per_step': int(len(items) * (3 * T * 3 + 3) * 4)},
                 'gpu_launches': net.seeker.engine().launches * (len(mine) // (2 * Q))}
         print(json.dumps(line), flush=True)

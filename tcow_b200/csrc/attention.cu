@@ -352,11 +352,16 @@ extern "C" int tcow_attn_spatial(const void* qkv, int64_t ld_qkv, void* out, int
   if ((ld_qkv % 8) || (ld_out % 8)) return set_error(TCOW_ERR_ARG, "attn_spatial: row pitches must be multiples of 8");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int S = N + (use_cls ? 1 : 0);
-  // Tensor-core (tcgen05/TMEM) kernel whenever one frame's keys fit its shared-memory stage; the mma.sync
-  // flash kernel below covers longer sequences (e.g. 480x640 frames, S = 1201).  TCOW_SPATIAL_IMPL=mma forces it.
-  static const bool force_mma = [] { const char* e = getenv("TCOW_SPATIAL_IMPL"); return e && e[0] == 'm'; }();
-  if (S <= 304 && (ld_qkv % 8) == 0 && !force_mma)
-    return launch_spatial_tc(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
+  // Tensor-core (tcgen05/TMEM) kernels: K/V resident in shared memory whenever one frame's keys fit (S <= 304), else
+  // streamed in 128-key blocks (e.g. 480x640 frames, S = 1201).  TCOW_SPATIAL_IMPL=mma forces the mma.sync flash kernel
+  // below (kept as an independent implementation for A/B checks), =stream forces the streamed kernel for every S.
+  static const char impl = [] { const char* e = getenv("TCOW_SPATIAL_IMPL"); return e ? e[0] : '\0'; }();
+  const bool force_mma = impl == 'm';
+  if (!force_mma && (ld_qkv % 8) == 0) {
+    if (S <= 304 && impl != 's')
+      return launch_spatial_tc(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
+    return launch_spatial_stream(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
+  }
   // pick the query-block width that wastes the fewest padded query rows (ties -> wider block)
   const int pad10 = ((S + 319) / 320) * 320, pad4 = ((S + 127) / 128) * 128;
   if (pad10 <= pad4) return launch_spatial<10>(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);

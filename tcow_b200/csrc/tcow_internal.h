@@ -16,4 +16,7 @@ int make_tmap_2d(void* map, bool is_f32, const void* ptr, uint64_t inner, uint64
 // tcgen05/TMEM spatial attention (attn_spatial_tc.cu); valid for N + use_cls <= 304.
 int launch_spatial_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N, int T,
                       int heads, int use_cls, int64_t cls_row0, cudaStream_t stream, float* lse = nullptr);
+// tcgen05/TMEM spatial attention with K/V streamed in 128-key blocks (flash attention): any N.
+int launch_spatial_stream(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N, int T,
+                          int heads, int use_cls, int64_t cls_row0, cudaStream_t stream);
 }  // namespace tcow

@@ -117,7 +117,9 @@ def run_sweep(net, items: Sequence[SweepItem], get_video, get_query, get_target,
         if v not in vcache:
             vcache.clear()
             tcache.clear()
-            vcache[v] = get_video(v).to(device, non_blocking=True)
+            vid = get_video(v).to(device, non_blocking=True)
+            # decoded frames arrive as uint8 (data/data_plugin.py:174 divides by 255 on the host): expand on the device
+            vcache[v] = vid.float().div_(255.0) if vid.dtype == torch.uint8 else vid.float()
         return vcache[v]
 
     def target_on_device(v, q):
