@@ -168,14 +168,30 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
   }
 }
 
-// out[n] (+)= sum_p partial[p*stride + n]
-__global__ void finalize_sum_kernel(const float* __restrict__ partial, int P, int64_t stride, float* __restrict__ out, int n,
-                                    int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int p = 0; p < P; ++p) s += partial[p * stride + i];
-  out[i] = accumulate ? out[i] + s : s;
+// out[n] (+)= sum_p partial[p*stride + n].  Block = 32 columns x 8 warps; the warps split the P partials (P is up to a
+// few hundred), then combine through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) finalize_sum_kernel(const float* __restrict__ partial, int P, int64_t stride,
+                                                           float* __restrict__ out, int n, int accumulate) {
+  __shared__ float s_red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (i < n) {
+    int p = warp;
+    for (; p + 8 < P; p += 16) {
+      s0 += partial[p * stride + i];
+      s1 += partial[(p + 8) * stride + i];
+    }
+    if (p < P) s0 += partial[p * stride + i];
+  }
+  s_red[warp][lane] = s0 + s1;
+  __syncthreads();
+  if (warp == 0 && i < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[w][lane];
+    out[i] = accumulate ? out[i] + s : s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- column sums
@@ -386,8 +402,8 @@ static int launch_ln_bwd(const void* dy, const void* xhat, const float* rstd, co
                                                  rstd, gamma, G, static_cast<__nv_bfloat16*>(Gb), ws, rows, accumulate);
   int rc = check_launch("layernorm_bwd_kernel");
   if (rc) return rc;
-  finalize_sum_kernel<<<(D + 255) / 256, 256, 0, s>>>(ws, blocks, 2 * D, dgamma, D, 1);
-  finalize_sum_kernel<<<(D + 255) / 256, 256, 0, s>>>(ws + D, blocks, 2 * D, dbeta, D, 1);
+  finalize_sum_kernel<<<(D + 31) / 32, 256, 0, s>>>(ws, blocks, 2 * D, dgamma, D, 1);
+  finalize_sum_kernel<<<(D + 31) / 32, 256, 0, s>>>(ws + D, blocks, 2 * D, dbeta, D, 1);
   return check_launch("finalize_sum_kernel");
 }
 
@@ -442,7 +458,7 @@ extern "C" int tcow_colsum_bf16(const void* x, int64_t ldx, int rows, int N, flo
   colsum_bf16_kernel<<<dim3((N + 255) / 256, chunks), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, rows, N, workspace);
   int rc = check_launch("colsum_bf16_kernel");
   if (rc) return rc;
-  finalize_sum_kernel<<<(N + 255) / 256, 256, 0, s>>>(workspace, chunks, N, out, N, accumulate);
+  finalize_sum_kernel<<<(N + 31) / 32, 256, 0, s>>>(workspace, chunks, N, out, N, accumulate);
   return check_launch("finalize_sum_kernel");
 }
 
@@ -456,9 +472,9 @@ extern "C" int tcow_embed_bwd(const float* G, float* dpos, float* dtime, float* 
   if (chunks > 16) chunks = 16;
   if (static_cast<int64_t>(chunks) * T * D > tcow_train_workspace_floats(0)) return set_error(TCOW_ERR_ARG, "embed_bwd: workspace too small");
   embed_bwd_time_kernel<<<dim3(T, chunks), 192, 0, s>>>(G, workspace, B * N, T, D);
-  finalize_sum_kernel<<<(T * D + 255) / 256, 256, 0, s>>>(workspace, chunks, static_cast<int64_t>(T) * D, dtime, T * D, accumulate);
+  finalize_sum_kernel<<<(T * D + 31) / 32, 256, 0, s>>>(workspace, chunks, static_cast<int64_t>(T) * D, dtime, T * D, accumulate);
   if (dcls_pos0)  // d(cls_token) = d(pos_embed[0]) = sum_b G[M + b]
-    finalize_sum_kernel<<<(D + 255) / 256, 256, 0, s>>>(G + static_cast<int64_t>(B) * N * T * D, B, D, dcls_pos0, D, accumulate);
+    finalize_sum_kernel<<<(D + 31) / 32, 256, 0, s>>>(G + static_cast<int64_t>(B) * N * T * D, B, D, dcls_pos0, D, accumulate);
   return check_launch("embed_bwd");
 }
 

@@ -1,3 +1,2 @@
-for grp in gemm_add_scaled scale_rows; do timeout 300 python tools/gpu_diag_train.py $grp 2>&1 | tail -12; done > gpurun_out/diag_train3.txt 2>&1
-timeout 900 python -m pytest tests/test_train_gpu.py -q 2>&1 | tail -40 > gpurun_out/train_gpu3.txt
-cat gpurun_out/diag_train3.txt gpurun_out/train_gpu3.txt
+TCOW_B200_LIB=$PWD/tcow_b200/libtcow_b200_w8.so timeout 300 python tools/gpu_diag_train.py attn_spatial_bwd_301 2>&1 | tail -4
+TCOW_B200_LIB=$PWD/tcow_b200/libtcow_b200_w8.so timeout 600 python tools/train_bench.py --profile 2>&1 | head -5
