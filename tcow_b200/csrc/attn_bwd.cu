@@ -11,6 +11,7 @@
 // in A-fragment layout — no transposes, no atomics, deterministic.  Gradients are staged per warp and written as
 // 128-byte rows into the canonical token-row layout of the qkv gradient (the dY operand of the qkv weight GEMMs).
 #include <math.h>
+#include <stdlib.h>
 
 #include "attn_frag.cuh"
 #include "ptx.cuh"
@@ -496,6 +497,12 @@ extern "C" int tcow_attn_spatial_bwd(const void* qkv, int64_t ld_qkv, const void
     return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: %d tokens per frame > %d not supported in training", N + (use_cls ? 1 : 0), SPB_ROWS);
   if ((ld_qkv % 8) || (ld_out % 8) || (ld_do % 8) || (ld_dqkv % 8)) return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: pitches must be multiples of 8");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // tcgen05/TMEM kernels (attn_spatial_bwd_tc.cu) by default; TCOW_SPATIAL_BWD_IMPL=mma selects the mma.sync kernel below
+  // (the independent implementation the tensor-memory kernels are tested against).
+  static const bool force_mma = [] { const char* e = getenv("TCOW_SPATIAL_BWD_IMPL"); return e && e[0] == 'm'; }();
+  if (!force_mma)
+    return launch_spatial_bwd_tc(qkv, ld_qkv, out, ld_out, out_cls, d_out, ld_do, d_out_cls, lse, d_qkv, ld_dqkv, d_cls, B,
+                                 N, T, heads, use_cls ? 1 : 0, cls_row0, s);
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);

@@ -774,7 +774,7 @@ attn_spatial_stream_kernel(const __grid_constant__ CUtensorMap tmFull, const __g
 }
 
 // 4-D view of the patch rows of qkv: (column, t, n, b) -> ((b*N+n)*T+t)*ld + column; box = 64 columns x box_n tokens.
-static int make_patch_tmap(CUtensorMap* m, const void* qkv, int64_t ld, int cols, int B, int N, int T, int box_n) {
+int make_patch_tmap(void* m, const void* qkv, int64_t ld, int cols, int B, int N, int T, int box_n) {
   const uint64_t dims[4] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(T), static_cast<uint64_t>(N),
                             static_cast<uint64_t>(B)};
   const uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(T) * ld * 2,

@@ -1,2 +1,4 @@
-TCOW_B200_LIB=$PWD/tcow_b200/libtcow_b200_w8.so timeout 300 python tools/gpu_diag_train.py attn_spatial_bwd_301 2>&1 | tail -4
-TCOW_B200_LIB=$PWD/tcow_b200/libtcow_b200_w8.so timeout 600 python tools/train_bench.py --profile 2>&1 | head -5
+timeout 300 python tools/gpu_diag_train.py attn_spatial_bwd > gpurun_out/diag_bwd_tc.txt 2>&1
+TCOW_SPATIAL_BWD_IMPL=mma timeout 300 python tools/gpu_diag_train.py attn_spatial_bwd_301 > gpurun_out/diag_bwd_mma.txt 2>&1
+tail -12 gpurun_out/diag_bwd_tc.txt; tail -3 gpurun_out/diag_bwd_mma.txt
+timeout 600 python tools/train_bench.py --profile 2>&1 | head -6
