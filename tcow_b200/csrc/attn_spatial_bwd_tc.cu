@@ -275,7 +275,7 @@ attn_spatial_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQf, const __grid
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const float sc = a.scale_log2, scale = a.scale;
+    const float sc = a.scale_log2, log2_scale = log2f(a.scale);
     uint32_t s_ct = 0, o_ct = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int h = item % heads, t = (item / heads) % T, b = item / (heads * T);
@@ -283,6 +283,8 @@ attn_spatial_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQf, const __grid
         const int tok = 128 * j + row;
         float lse, Dv;
         row_stats(a, item, b, t, h, tok, S, lse, Dv);
+        const float lse_s = lse - log2_scale;  // folds the 1/sqrt(hd) factor of dS into the exponent
+        const uint64_t sc2 = f2_pack(sc, sc), nl2 = f2_pack(-lse_s, -lse_s), nD2 = f2_pack(-Dv, -Dv);
         for (int blk = 0; blk < nblk; ++blk, ++s_ct) {
           const int nkb = (S16 - blk * BQ_KB) < BQ_KB ? (S16 - blk * BQ_KB) : BQ_KB;
           mbar_wait(s_full, s_ct & 1);
@@ -293,14 +295,27 @@ attn_spatial_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQf, const __grid
             tmem_ld_32x32(t_lane + BQ_KB + 32 * c, vp);
             tmem_ld_wait();
             const int key0 = blk * BQ_KB + 32 * c;
+            if (key0 + 32 <= S) {
+              // packed fp32x2: dS = 2^(s c - lse + log2(scale)) * (dP - D): 3 issue slots per element pair + 2 MUFU
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const bool ok0 = key0 + e < S, ok1 = key0 + e + 1 < S;
-              const float p0 = ex2a(fmaf(__uint_as_float(vs[e]), sc, -lse));
-              const float p1 = ex2a(fmaf(__uint_as_float(vs[e + 1]), sc, -lse));
-              const float d0 = ok0 ? p0 * (__uint_as_float(vp[e]) - Dv) * scale : 0.f;
-              const float d1 = ok1 ? p1 * (__uint_as_float(vp[e + 1]) - Dv) * scale : 0.f;
-              pk[e >> 1] = pack_bf16(d0, d1);
+              for (int e = 0; e < 32; e += 2) {
+                float x0, x1;
+                f2_unpack(f2_fma(f2_pack_u(vs[e], vs[e + 1]), sc2, nl2), x0, x1);
+                const uint64_t p2 = f2_pack(ex2a(x0), ex2a(x1));
+                float d0, d1;
+                f2_unpack(f2_mul(p2, f2_add(f2_pack_u(vp[e], vp[e + 1]), nD2)), d0, d1);
+                pk[e >> 1] = pack_bf16(d0, d1);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                const bool ok0 = key0 + e < S, ok1 = key0 + e + 1 < S;
+                const float p0 = ex2a(fmaf(__uint_as_float(vs[e]), sc, -lse_s));
+                const float p1 = ex2a(fmaf(__uint_as_float(vs[e + 1]), sc, -lse_s));
+                const float d0 = ok0 ? p0 * (__uint_as_float(vp[e]) - Dv) : 0.f;
+                const float d1 = ok1 ? p1 * (__uint_as_float(vp[e + 1]) - Dv) : 0.f;
+                pk[e >> 1] = pack_bf16(d0, d1);
+              }
             }
             tmem_st_32x16(t_lane + 16 * c, pk);  // dS over S columns already consumed
           }
@@ -475,15 +490,16 @@ attn_spatial_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQf, const __gri
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sc = a.scale_log2, scale = a.scale;
+    const uint64_t sc2 = f2_pack(sc, sc), scale2 = f2_pack(scale, scale);
     uint32_t s_ct = 0, acc_ct = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int h = item % heads, t = (item / heads) % T, b = item / (heads * T);
-      // per-query statistics of this frame -> shared memory (queries past S: lse = +inf -> p = 0)
+      // per-query statistics of this frame -> shared memory (queries past S: -lse = -inf -> p = 0)
       for (int q = row; q < BK_STAT; q += 128) {
         float lse, Dv;
         row_stats(a, item, b, t, h, q, S, lse, Dv);
-        s_lse[q] = q < S ? lse : INFINITY;
-        s_D[q] = Dv;
+        s_lse[q] = q < S ? -lse : -INFINITY;   // stored negated: the addend of the exponent FMA
+        s_D[q] = -Dv * scale;                  // and of the (dP scale - D scale) FMA
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int kt = 0; kt < nkt; ++kt, ++acc_ct) {
@@ -499,22 +515,28 @@ attn_spatial_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQf, const __gri
             tmem_ld_32x32(t_lane + BK_QB + 32 * c, vp);
             tmem_ld_wait();
             const int q0 = qb * BK_QB + 32 * c;
+            if (kvalid) {
+              // packed fp32x2: P^T = 2^(s c - lse_q), dS^T = P^T * (dP^T scale - D_q scale); -lse_q and -D_q*scale come
+              // from shared memory (same address in every lane: broadcast)
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(s_lse + q0 + e);   // same address in every lane: broadcast
-              const float4 d4 = *reinterpret_cast<const float4*>(s_D + q0 + e);
-              const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq[4] = {d4.x, d4.y, d4.z, d4.w};
-              float p[4], ds[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                p[u] = kvalid ? ex2a(fmaf(__uint_as_float(vs[e + u]), sc, -lq[u])) : 0.f;
-                ds[u] = p[u] * (__uint_as_float(vp[e + u]) - dq[u]) * scale;
-                if (!(p[u] > 0.f)) ds[u] = 0.f;   // masked entries stay exactly zero whatever the stale dP holds
+              for (int e = 0; e < 32; e += 4) {
+                const float4 l4 = *reinterpret_cast<const float4*>(s_lse + q0 + e);
+                const float4 d4 = *reinterpret_cast<const float4*>(s_D + q0 + e);
+                float x0, x1, x2, x3;
+                f2_unpack(f2_fma(f2_pack_u(vs[e], vs[e + 1]), sc2, f2_pack(l4.x, l4.y)), x0, x1);
+                f2_unpack(f2_fma(f2_pack_u(vs[e + 2], vs[e + 3]), sc2, f2_pack(l4.z, l4.w)), x2, x3);
+                const float p0 = ex2a(x0), p1 = ex2a(x1), p2 = ex2a(x2), p3 = ex2a(x3);
+                float r0, r1, r2, r3;
+                f2_unpack(f2_mul(f2_pack(p0, p1), f2_fma(f2_pack_u(vp[e], vp[e + 1]), scale2, f2_pack(d4.x, d4.y))), r0, r1);
+                f2_unpack(f2_mul(f2_pack(p2, p3), f2_fma(f2_pack_u(vp[e + 2], vp[e + 3]), scale2, f2_pack(d4.z, d4.w))), r2, r3);
+                pp[e >> 1] = pack_bf16(p0, p1);
+                pp[(e >> 1) + 1] = pack_bf16(p2, p3);
+                pd[e >> 1] = pack_bf16(r0, r1);
+                pd[(e >> 1) + 1] = pack_bf16(r2, r3);
               }
-              pp[e >> 1] = pack_bf16(p[0], p[1]);
-              pp[(e >> 1) + 1] = pack_bf16(p[2], p[3]);
-              pd[e >> 1] = pack_bf16(ds[0], ds[1]);
-              pd[(e >> 1) + 1] = pack_bf16(ds[2], ds[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pp[e] = pd[e] = 0u;
             }
             tmem_st_32x16(t_lane + 16 * c, pp);            // P^T over consumed S^T columns
             tmem_st_32x16(t_lane + BK_QB + 16 * c, pd);    // dS^T over consumed dP^T columns

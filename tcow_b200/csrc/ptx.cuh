@@ -27,6 +27,9 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------- mbarrier
+#ifndef TCOW_MBAR_HINT_NS
+#define TCOW_MBAR_HINT_NS 1000000u  // suspend-time hint of mbarrier.try_wait (ns)
+#endif
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -48,7 +51,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(1000000u)
+      : "r"(bar), "r"(parity), "r"(TCOW_MBAR_HINT_NS)
       : "memory");
   return ok != 0;
 }
