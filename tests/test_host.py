@@ -142,3 +142,33 @@ def test_merged_temporal_projection_is_algebraically_exact(net):
     assert (F.linear(o, W, b) - ref).abs().max() < 1e-12
     pk = SeekerEngine(mod)._pack(mod, torch.device('cpu'))
     assert (pk.blocks[3].t_out[0].double() - W).abs().max() < 2e-4       # one bf16 rounding of |W| ~ 0.02
+
+
+def test_checkpoint_round_trip_in_reference_format(tmp_path, logger):
+    """train.py:269-304 layout -> tcow_b200.checkpoint.load_networks (eval/inference.py:19-57 signature)."""
+    import argparse
+
+    from tcow_b200 import checkpoint
+    T, Hf, Wf = 4, 32, 48
+    seeker_args = dict(num_total_frames=T, num_visible_frames=T, frame_height=Hf, frame_width=Wf, tracker_pretrained='1',
+                       attention_type='divided_space_time', patch_size=16, causal_attention=1, norm_embeddings=False,
+                       drop_path_rate=0.1, network_depth=12, track_map_stride=4, track_map_resize='bilinear',
+                       query_channels=1, output_channels=3, flag_channels=3)
+    sd = synth.make_state_dict(901, num_frames=T, frame_height=Hf, frame_width=Wf)
+    net = checkpoint.build_seeker(logger, seeker_args, sd)
+    assert net.seeker.tracker_backbone.pretrained is True          # RGB normalisation flag without any download
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
+    train_args = argparse.Namespace(name='unit', num_frames=T, learn_rate=1e-4)   # a Namespace: needs weights_only=False
+    path = checkpoint.save_model_checkpoint(str(tmp_path), 7, train_args, {'dset': 1}, seeker_args, {'seeker': net},
+                                            {'seeker': opt})
+    raw = torch.load(path, map_location='cpu', weights_only=False)
+    assert set(raw) >= {'epoch', 'train_args', 'dset_args', 'seeker_args', 'net_seeker', 'optim_seeker'}
+    assert len(raw['net_seeker']) == 251
+    (networks, targs, dargs, margs, epoch) = checkpoint.load_networks(str(tmp_path), 'cpu', logger)
+    assert epoch == 7 and targs.name == 'unit' and dargs == {'dset': 1} and margs['seeker'] == seeker_args
+    got = networks['seeker'].state_dict()
+    assert list(got) == list(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    assert networks['seeker'].seeker.tracker_backbone.pretrained is True
+    assert open(tmp_path / 'checkpoint_epoch.txt').read().strip() == '7'
+    off = dict(seeker_args, tracker_pretrained='0')
+    assert checkpoint.build_seeker(logger, off).seeker.tracker_backbone.pretrained is False
