@@ -138,23 +138,50 @@ class SeekerTrainEngine:
         pk.pos = f32(bb.pos_embed).reshape(-1, D).contiguous()
         pk.time = f32(bb.time_embed).reshape(-1, D).contiguous()
         pk.cls = f32(bb.cls_token).reshape(D).contiguous()
+        # Per weight type, the 12 blocks are packed together: one stack, one bf16 cast and one transposing cast per type
+        # (about 40 small launches per step instead of 300).
+        blocks = list(bb.blocks)
+        nb = len(blocks)
+
+        def packed_linear(get):
+            W = torch.stack([f32(get(blk).weight) for blk in blocks])                     # [nb, out, in] fp32
+            Wb = W.to(torch.bfloat16)
+            Wt = torch.empty((nb, W.shape[2], W.shape[1]), device=device, dtype=torch.bfloat16)
+            Wt.copy_(W.transpose(1, 2))                                                    # cast + transpose in one pass
+            bias = [f32(get(blk).bias).contiguous() for blk in blocks]
+            return [(Wb[i], bias[i], Wt[i]) for i in range(nb)]
+
+        t_qkv = packed_linear(lambda blk: blk.temporal_attn.qkv)
+        s_qkv = packed_linear(lambda blk: blk.attn.qkv)
+        s_proj = packed_linear(lambda blk: blk.attn.proj)
+        fc1 = packed_linear(lambda blk: blk.mlp.fc1)
+        fc2 = packed_linear(lambda blk: blk.mlp.fc2)
+        Wp_all = torch.stack([f32(blk.temporal_attn.proj.weight) for blk in blocks])
+        bp_all = torch.stack([f32(blk.temporal_attn.proj.bias) for blk in blocks])
+        Wf_all = torch.stack([f32(blk.temporal_fc.weight) for blk in blocks])
+        bf_all = torch.stack([f32(blk.temporal_fc.bias) for blk in blocks])
+        if self.merge_temporal_proj:   # fc(proj(o)) = o (Wf Wp)^T + (Wf bp + bf)   (vit.py:111 -> :174, no nonlinearity)
+            Wm_all = _mm(Wf_all, Wp_all)                                                   # batched fp32 product
+            b1_all = _mm(Wf_all, bp_all[:, :, None])[:, :, 0].contiguous()                 # the bias part inside DropPath
+            bm_all = b1_all + bf_all
+            Wm_b = Wm_all.to(torch.bfloat16)
+            Wm_t = torch.empty_like(Wm_b)
+            Wm_t.copy_(Wm_all.transpose(1, 2))
+        else:
+            t_proj = packed_linear(lambda blk: blk.temporal_attn.proj)
+            t_fc = packed_linear(lambda blk: blk.temporal_fc)
         pk.blocks = []
-        for blk in bb.blocks:
+        pk.raw_t_all = (Wp_all, bp_all, Wf_all, bf_all)
+        for i, blk in enumerate(blocks):
             w = _W()
             ln = lambda m: (f32(m.weight).contiguous(), f32(m.bias).contiguous())
             w.tn1, w.n1, w.n2 = ln(blk.temporal_norm1), ln(blk.norm1), ln(blk.norm2)
-            lin = lambda m: (bf(f32(m.weight)), f32(m.bias).contiguous(), bft(f32(m.weight)))   # (W, b, W^T)
-            w.t_qkv, w.s_qkv, w.s_proj = lin(blk.temporal_attn.qkv), lin(blk.attn.qkv), lin(blk.attn.proj)
-            w.fc1, w.fc2 = lin(blk.mlp.fc1), lin(blk.mlp.fc2)
-            Wp, bp = f32(blk.temporal_attn.proj.weight), f32(blk.temporal_attn.proj.bias)
-            Wf, bfc = f32(blk.temporal_fc.weight), f32(blk.temporal_fc.bias)
-            w.raw_t = (Wp, bp, Wf, bfc)
-            if self.merge_temporal_proj:   # fc(proj(o)) = o (Wf Wp)^T + (Wf bp + bf)   (vit.py:111 -> :174, no nonlinearity)
-                Wm = _mm(Wf, Wp)
-                b1 = _mm(Wf, bp[:, None])[:, 0].contiguous()        # the part of the bias that sits inside DropPath
-                w.t_out = (bf(Wm), (b1 + bfc).contiguous(), bft(Wm), b1, bfc.contiguous())
+            w.t_qkv, w.s_qkv, w.s_proj, w.fc1, w.fc2 = t_qkv[i], s_qkv[i], s_proj[i], fc1[i], fc2[i]
+            w.raw_t = (Wp_all[i], bp_all[i], Wf_all[i], bf_all[i])
+            if self.merge_temporal_proj:
+                w.t_out = (Wm_b[i], bm_all[i], Wm_t[i], b1_all[i], bf_all[i])
             else:
-                w.t_proj, w.t_fc = lin(blk.temporal_attn.proj), lin(blk.temporal_fc)
+                w.t_proj, w.t_fc = t_proj[i], t_fc[i]
             pk.blocks.append(w)
         pk.norm = (f32(bb.norm.weight).contiguous(), f32(bb.norm.bias).contiguous())
         C, s = mod.output_channels, max(int(mod.track_map_stride), 1)
@@ -497,19 +524,26 @@ class SeekerTrainEngine:
             for ours, theirs in (('t_qkv', 'temporal_attn.qkv'), ('s_qkv', 'attn.qkv'), ('s_proj', 'attn.proj'),
                                  ('fc1', 'mlp.fc1'), ('fc2', 'mlp.fc2')):
                 g[q + theirs + '.weight'], g[q + theirs + '.bias'] = gv(p + ours + '_w'), gv(p + ours + '_b')
-            if merged:
-                # W_m = Wf Wp, b_m = Wf bp + bf  =>  dWf = dW_m Wp^T + db_m bp^T, dWp = Wf^T dW_m, dbp = Wf^T db_m, dbf = db_m
-                # (under stochastic depth the Wf bp part of the bias is inside DropPath, bf outside: two bias gradients)
-                Wp, bp, Wf, _ = w.raw_t
-                dWm, dbm = gv(p + 't_out_w'), gv(p + 't_out_b')
-                dbf = gv(p + 't_out_b2') if (dropped is not None and dropped[i]) else dbm
-                g[q + 'temporal_fc.weight'] = _mm(dWm, Wp.t()) + dbm[:, None] * bp[None, :]
-                g[q + 'temporal_fc.bias'] = dbf
-                g[q + 'temporal_attn.proj.weight'] = _mm(Wf.t(), dWm)
-                g[q + 'temporal_attn.proj.bias'] = _mm(Wf.t(), dbm[:, None])[:, 0]
-            else:
+            if not merged:
                 g[q + 'temporal_fc.weight'], g[q + 'temporal_fc.bias'] = gv(p + 't_fc_w'), gv(p + 't_fc_b')
                 g[q + 'temporal_attn.proj.weight'], g[q + 'temporal_attn.proj.bias'] = gv(p + 't_proj_w'), gv(p + 't_proj_b')
+        if merged:
+            # W_m = Wf Wp, b_m = Wf bp + bf  =>  dWf = dW_m Wp^T + db_1 bp^T, dWp = Wf^T dW_m, dbp = Wf^T db_1, dbf = db_2
+            # (under stochastic depth the Wf bp part of the bias is inside DropPath, bf outside: two bias gradients;
+            # without it db_2 = db_1).  All 12 blocks in four batched fp32 products.
+            nb = len(pk.blocks)
+            Wp, bp, Wf, _ = pk.raw_t_all
+            dWm = torch.stack([gv(f'b{i}.t_out_w') for i in range(nb)])
+            dbm = torch.stack([gv(f'b{i}.t_out_b') for i in range(nb)])
+            dbf = torch.stack([gv(f'b{i}.t_out_b2') if (dropped is not None and dropped[i]) else gv(f'b{i}.t_out_b')
+                               for i in range(nb)])
+            dWf = _mm(dWm, Wp.transpose(1, 2)) + dbm[:, :, None] * bp[:, None, :]
+            dWp = _mm(Wf.transpose(1, 2), dWm)
+            dbp = _mm(Wf.transpose(1, 2), dbm[:, :, None])[:, :, 0]
+            for i in range(nb):
+                q = pre + f'blocks.{i}.'
+                g[q + 'temporal_fc.weight'], g[q + 'temporal_fc.bias'] = dWf[i], dbf[i]
+                g[q + 'temporal_attn.proj.weight'], g[q + 'temporal_attn.proj.bias'] = dWp[i], dbp[i]
         # head: undo the avg-pool fold (each pooled row is the mean of stride^2 rows of tracker_post_linear)
         C, pp, s = mod.output_channels, pk.pp, pk.stride
         n_mask = C * pp * pp

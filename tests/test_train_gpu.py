@@ -175,3 +175,25 @@ def test_stochastic_depth_draws(logger):
     assert scales[0] is None and all(s is not None for s in scales[1:])
     last = scales[-1]['rs_t']
     assert set(last.unique().tolist()) <= {0.0, 2.0}          # keep = 0.5 in the last block: survivors scaled by 2
+
+
+def test_backward_full_size_vs_oracle_autograd(logger):
+    """BASELINE's full shape (T=30, 240x320, 301 tokens per frame, causal): one sample, gradients of all 251 tensors
+    against the fp32 autograd of the oracle run on the host cores (about half a minute)."""
+    import os
+    T, Hf, Wf = 30, 240, 320
+    meta = dict(T=T, Hf=Hf, Wf=Wf, causal=1, weight_seed=901, samples=[3],
+                ref_kwargs=dict(num_total_frames=T, num_visible_frames=T, frame_height=Hf, frame_width=Wf,
+                                tracker_pretrained=False, attention_type='divided_space_time', patch_size=16,
+                                causal_attention=1, norm_embeddings=False, drop_path_rate=0.0, network_depth=12,
+                                track_map_stride=4, track_map_resize='bilinear', query_channels=1, output_channels=3,
+                                flag_channels=3))
+    net = build(logger, meta)
+    rgb, q, tm, tf = case_data(meta)
+    loss, grads, _ = our_grads(net, rgb, q, tm, tf)
+    torch.set_num_threads(os.cpu_count() or 8)
+    sd = cached_state_dict(901, T, Hf, Wf)
+    oloss, ref = mgg.oracle_grads(sd, meta, rgb, q, tm, tf)
+    assert abs(loss - oloss) < 5e-3
+    bad, wc, wr = compare(grads, ref)
+    assert not bad, f'{len(bad)} tensors out of tolerance (worst cos {wc:.5f}, rel {wr:.4f}): {bad[:8]}'
