@@ -46,6 +46,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // waiting warp costs (almost) no issue slots — important when two CTAs share an SM.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#ifdef TCOW_MBAR_SPIN  // experiment: plain polling (test_wait), no hardware suspend
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -59,7 +69,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef TCOW_MBAR_SPIN
+    if (++spins > 2000000000u) {
+#else
     if (++spins > 8000u) {  // each failed try_wait sleeps up to ~1 ms: a stuck protocol traps within seconds
+#endif
       printf("tcow: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);
       __trap();
