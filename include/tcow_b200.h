@@ -198,8 +198,8 @@ int tcow_attn_temporal_bwd(const void* qkv, int64_t ld_qkv, const void* out, int
                            void* stream);
 
 /* Backward of tcow_attn_spatial(_train).  out / d_out: patch rows (bf16); out_cls / d_out_cls: the cls query's
- * per-frame output and its gradient, [B,T,heads*64] fp32; lse from the forward; d_cls: scratch [B,T,3,heads*64]
- * fp32.  Writes d_qkv for every patch row and (summed over the frames) for row cls_row0+b. */
+ * per-frame output and its gradient, [B,T,heads*64] fp32; lse from the forward; d_cls: scratch of
+ * B*T*heads*(3*64 + 304) floats (per-frame cls gradients [B,T,3,heads*64], then dO.O per token [B*T*heads, 304]).  Writes d_qkv for every patch row and (summed over the frames) for row cls_row0+b. */
 int tcow_attn_spatial_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* out_cls,
                           const void* d_out, int64_t ld_do, const float* d_out_cls, const float* lse, void* d_qkv,
                           int64_t ld_dqkv, float* d_cls, int B, int N, int T, int heads, int use_cls, int64_t cls_row0,

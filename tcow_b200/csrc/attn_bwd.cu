@@ -492,7 +492,8 @@ extern "C" int tcow_attn_spatial_bwd(const void* qkv, int64_t ld_qkv, const void
   using namespace tcow;
   if (!qkv || !out || !d_out || !lse || !d_qkv || B <= 0 || N <= 0 || T <= 0 || heads <= 0)
     return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: bad argument");
-  if (use_cls && (!out_cls || !d_out_cls || !d_cls)) return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: cls buffers missing");
+  if (use_cls && (!out_cls || !d_out_cls)) return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: cls buffers missing");
+  if (!d_cls) return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: scratch missing");
   if (N + (use_cls ? 1 : 0) > SPB_ROWS)
     return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: %d tokens per frame > %d not supported in training", N + (use_cls ? 1 : 0), SPB_ROWS);
   if ((ld_qkv % 8) || (ld_out % 8) || (ld_do % 8) || (ld_dqkv % 8)) return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: pitches must be multiples of 8");
@@ -501,8 +502,9 @@ extern "C" int tcow_attn_spatial_bwd(const void* qkv, int64_t ld_qkv, const void
   // (the independent implementation the tensor-memory kernels are tested against).
   static const bool force_mma = [] { const char* e = getenv("TCOW_SPATIAL_BWD_IMPL"); return e && e[0] == 'm'; }();
   if (!force_mma)
-    return launch_spatial_bwd_tc(qkv, ld_qkv, out, ld_out, out_cls, d_out, ld_do, d_out_cls, lse, d_qkv, ld_dqkv, d_cls, B,
-                                 N, T, heads, use_cls ? 1 : 0, cls_row0, s);
+    return launch_spatial_bwd_tc(qkv, ld_qkv, out, ld_out, out_cls, d_out, ld_do, d_out_cls, lse, d_qkv, ld_dqkv, d_cls,
+                                 d_cls + static_cast<int64_t>(B) * T * 3 * heads * 64, B, N, T, heads, use_cls ? 1 : 0,
+                                 cls_row0, s);
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);

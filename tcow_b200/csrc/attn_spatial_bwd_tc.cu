@@ -36,6 +36,7 @@ struct BwdArgs {
   int64_t ld_do;
   const float* d_out_cls;
   const float* lse;
+  const float* dsum;   // D = dO . O per (item, token): written by attn_row_dot_kernel, laid out like lse
   __nv_bfloat16* d_qkv;
   int64_t ld_dqkv;
   float* d_cls;
@@ -59,34 +60,14 @@ __device__ __forceinline__ void st_smem_v4(uint32_t addr, uint32_t a, uint32_t b
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// D = dO . O and the base-2 lse of token `tok` of frame (b,t), head h (0 / 0 past S).  dO of the cls token is rounded to
-// bf16 first, as the tensor cores see it.
-__device__ __forceinline__ void row_stats(const BwdArgs& a, int item, int b, int t, int h, int tok, int S, float& lse,
-                                          float& Dv) {
-  const int N = a.N, D = a.heads * 64;
+// D = dO . O and the base-2 lse of token `tok` of work item `item` (0 / 0 past S): two 4-byte loads (attn_row_dot_kernel
+// has already reduced dO . O for every token and head).
+__device__ __forceinline__ void row_stats(const BwdArgs& a, int item, int tok, int S, float& lse, float& Dv) {
   lse = 0.f;
   Dv = 0.f;
   if (tok >= S) return;
   lse = __ldg(a.lse + static_cast<int64_t>(item) * BT_ROWS + tok);
-  float s = 0.f;
-  if (tok < N) {
-    const int64_t row = (static_cast<int64_t>(b) * N + tok) * a.T + t;
-    const uint4* o = reinterpret_cast<const uint4*>(a.out + row * a.ld_out + h * 64);
-    const uint4* d = reinterpret_cast<const uint4*>(a.d_out + row * a.ld_do + h * 64);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) s += dot8b(__ldg(d + c), __ldg(o + c));
-  } else {
-    const int64_t off = (static_cast<int64_t>(b) * a.T + t) * D + h * 64;
-    const float4* o = reinterpret_cast<const float4*>(a.out_cls + off);
-    const float4* d = reinterpret_cast<const float4*>(a.d_out_cls + off);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float4 ov = __ldg(o + c), dv = __ldg(d + c);
-      const uint32_t p0 = pack_bf16(dv.x, dv.y), p1 = pack_bf16(dv.z, dv.w);
-      s += bflo(p0) * ov.x + bfhi(p0) * ov.y + bflo(p1) * ov.z + bfhi(p1) * ov.w;
-    }
-  }
-  Dv = s;
+  Dv = __ldg(a.dsum + static_cast<int64_t>(item) * BT_ROWS + tok);
 }
 
 // cls token rows (token N of the frame) into row `r` of swizzled [rows][64] bf16 tiles: lanes 0-7 copy 16-byte chunks.
@@ -282,7 +263,7 @@ attn_spatial_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQf, const __grid
       for (int j = 0; j < nq; ++j, ++o_ct) {
         const int tok = 128 * j + row;
         float lse, Dv;
-        row_stats(a, item, b, t, h, tok, S, lse, Dv);
+        row_stats(a, item, tok, S, lse, Dv);
         const float lse_s = lse - log2_scale;  // folds the 1/sqrt(hd) factor of dS into the exponent
         const uint64_t sc2 = f2_pack(sc, sc), nl2 = f2_pack(-lse_s, -lse_s), nD2 = f2_pack(-Dv, -Dv);
         for (int blk = 0; blk < nblk; ++blk, ++s_ct) {
@@ -497,7 +478,7 @@ attn_spatial_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQf, const __gri
       // per-query statistics of this frame -> shared memory (queries past S: -lse = -inf -> p = 0)
       for (int q = row; q < BK_STAT; q += 128) {
         float lse, Dv;
-        row_stats(a, item, b, t, h, q, S, lse, Dv);
+        row_stats(a, item, q, S, lse, Dv);
         s_lse[q] = q < S ? -lse : -INFINITY;   // stored negated: the addend of the exponent FMA
         s_D[q] = -Dv * scale;                  // and of the (dP scale - D scale) FMA
       }
@@ -570,6 +551,41 @@ attn_spatial_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQf, const __gri
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
+// D[(b*T+t)*heads+h][tok] = sum_d dO[tok, h*64+d] * O[tok, h*64+d] for every patch token (one warp per token row: 96
+// 16-byte vectors, 8 lanes per head) and, in the last blocks, for the cls token (fp32 O / dO, dO rounded to bf16 as the
+// tensor cores see it).  Both backward passes then read D like the lse.
+__global__ void __launch_bounds__(256) attn_row_dot_kernel(const BwdArgs a, float* __restrict__ dsum) {
+  const int lane = threadIdx.x & 31;
+  const int N = a.N, T = a.T, heads = a.heads, D = heads * 64;
+  const int64_t M = static_cast<int64_t>(a.B) * N * T;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row < M) {
+    const int t = static_cast<int>(row % T), n = static_cast<int>((row / T) % N), b = static_cast<int>(row / (static_cast<int64_t>(T) * N));
+    const uint4* o = reinterpret_cast<const uint4*>(a.out + row * a.ld_out);
+    const uint4* d = reinterpret_cast<const uint4*>(a.d_out + row * a.ld_do);
+    for (int v = lane; v < D / 8; v += 32) {
+      float s = dot8b(__ldg(d + v), __ldg(o + v));
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if ((lane & 7) == 0) dsum[((static_cast<int64_t>(b) * T + t) * heads + (v >> 3)) * BT_ROWS + n] = s;
+    }
+  } else if (a.use_cls) {
+    const int64_t c = row - M;  // (b*T + t)*heads + h
+    if (c < static_cast<int64_t>(a.B) * T * heads) {
+      const int h = static_cast<int>(c % heads);
+      const int64_t bt = c / heads;
+      const float2 ov = __ldg(reinterpret_cast<const float2*>(a.out_cls + bt * D + h * 64) + lane);
+      const float2 dv = __ldg(reinterpret_cast<const float2*>(a.d_out_cls + bt * D + h * 64) + lane);
+      const uint32_t p = pack_bf16(dv.x, dv.y);
+      float s = bflo(p) * ov.x + bfhi(p) * ov.y;
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+      if (lane == 0) dsum[c * BT_ROWS + N] = s;
+    }
+  }
+}
+
 // d_qkv[cls_row0+b, :] (bf16) = sum_t d_cls[b,t,:]   (3*D columns)
 __global__ void cls_grad_reduce_tc_kernel(const float* __restrict__ d_cls, __nv_bfloat16* __restrict__ d_qkv, int64_t ld, int T,
                                           int cols, int64_t cls_row0) {
@@ -583,8 +599,8 @@ __global__ void cls_grad_reduce_tc_kernel(const float* __restrict__ d_cls, __nv_
 
 int launch_spatial_bwd_tc(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* out_cls,
                           const void* d_out, int64_t ld_do, const float* d_out_cls, const float* lse, void* d_qkv,
-                          int64_t ld_dqkv, float* d_cls, int B, int N, int T, int heads, int use_cls, int64_t cls_row0,
-                          cudaStream_t stream) {
+                          int64_t ld_dqkv, float* d_cls, float* dsum, int B, int N, int T, int heads, int use_cls,
+                          int64_t cls_row0, cudaStream_t stream) {
   alignas(64) CUtensorMap q128, q128t, q256, q256t, d128, d128t, d256, d256t;
   const int cols = 3 * heads * 64, dcols = heads * 64;
   const int t128 = N % 128, f256 = N < 256 ? N : 256, t256 = N - f256;
@@ -607,9 +623,15 @@ int launch_spatial_bwd_tc(const void* qkv, int64_t ld_qkv, const void* out, int6
     configured[dev & 63] = true;
   }
   const BwdArgs a{static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<const __nv_bfloat16*>(out), ld_out, out_cls,
-                  static_cast<const __nv_bfloat16*>(d_out), ld_do, d_out_cls, lse, static_cast<__nv_bfloat16*>(d_qkv), ld_dqkv,
-                  d_cls, B, N, T, heads, use_cls, cls_row0, 0.125f * 1.4426950408889634f, 0.125f};
+                  static_cast<const __nv_bfloat16*>(d_out), ld_do, d_out_cls, lse, dsum, static_cast<__nv_bfloat16*>(d_qkv),
+                  ld_dqkv, d_cls, B, N, T, heads, use_cls, cls_row0, 0.125f * 1.4426950408889634f, 0.125f};
   const int items = B * T * heads;
+  {
+    const int64_t rows = static_cast<int64_t>(B) * N * T + (use_cls ? static_cast<int64_t>(items) : 0);
+    attn_row_dot_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(a, dsum);
+    rc = check_launch("attn_row_dot_kernel");
+    if (rc) return rc;
+  }
   const int slots = 2 * sm_count();
   const int grid = items < slots ? items : slots;
   attn_spatial_bwd_q_kernel<<<grid, 256, BQ_SMEM, stream>>>(q128, q128t, q256, q256t, d128, d128t, a);

@@ -22,8 +22,8 @@ int make_patch_tmap(void* map, const void* base, int64_t ld, int cols, int B, in
 // tcgen05/TMEM backward of the spatial attention (attn_spatial_bwd_tc.cu); valid for N + use_cls <= 304.
 int launch_spatial_bwd_tc(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* out_cls,
                           const void* d_out, int64_t ld_do, const float* d_out_cls, const float* lse, void* d_qkv,
-                          int64_t ld_dqkv, float* d_cls, int B, int N, int T, int heads, int use_cls, int64_t cls_row0,
-                          cudaStream_t stream);
+                          int64_t ld_dqkv, float* d_cls, float* dsum, int B, int N, int T, int heads, int use_cls,
+                          int64_t cls_row0, cudaStream_t stream);
 // tcgen05/TMEM spatial attention with K/V streamed in 128-key blocks (flash attention): any N.
 int launch_spatial_stream(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N, int T,
                           int heads, int use_cls, int64_t cls_row0, cudaStream_t stream);

@@ -225,9 +225,16 @@ def attn_temporal_bwd(qkv, out, d_out, d_qkv, num_seq, T, heads, causal_diag):
     return d_qkv
 
 
+def spatial_bwd_scratch_floats(B, T, heads):
+    """fp32 scratch of tcow_attn_spatial_bwd: per-frame cls gradients [B,T,3,heads*64] + dO.O per token [B*T*heads,304]."""
+    return B * T * heads * (3 * 64 + 304)
+
+
 def attn_spatial_bwd(qkv, out, out_cls, d_out, d_out_cls, lse, d_qkv, d_cls, B, N, T, heads, use_cls, cls_row0):
     for t, n in ((qkv, 'qkv'), (out, 'out'), (d_out, 'd_out'), (d_qkv, 'd_qkv')):
         _chk(t, torch.bfloat16, 'attn_spatial_bwd.' + n)
+    if d_cls is None or d_cls.numel() < spatial_bwd_scratch_floats(B, T, heads):
+        raise ValueError('attn_spatial_bwd: scratch must hold spatial_bwd_scratch_floats(B, T, heads) floats')
     _lib.call('tcow_attn_spatial_bwd', qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), _p(out_cls),
               d_out.data_ptr(), d_out.stride(0), _p(d_out_cls), lse.data_ptr(), d_qkv.data_ptr(), d_qkv.stride(0),
               _p(d_cls), B, N, T, heads, int(use_cls), cls_row0, _stream())

@@ -454,10 +454,10 @@ class SeekerTrainEngine:
                     colsum(Gs[:Rs], p + 's_proj_b')
                 WG('wgrad_proj', Gs[:Rs], s.O_s, gv(p + 's_proj_w'))
                 G('dgrad_proj', Gs[:Rs], w.s_proj[2], None, dO[:Rs], EPI_BF16)
-                dOCLS = dCLS = None
+                dOCLS = None
+                dCLS = torch.empty((ops.spatial_bwd_scratch_floats(B, T, HEADS),), device=device, dtype=torch.float32)
                 if use_cls:
                     dOCLS = torch.empty((B, T, D), device=device, dtype=torch.float32)
-                    dCLS = torch.empty((B, T, 3, D), device=device, dtype=torch.float32)
                     L('cls_merge_bwd', ops.cls_merge_bwd, dO, dOCLS, B, T, D, M, 0 if causal == 0 else 1)
                     if dp is not None and causal == 0:
                         dOCLS.mul_(dp['ss'].view(B, T, 1))

@@ -234,9 +234,9 @@ def check_attn_spatial_bwd(B, N, T, use_cls, cls_mode=1, heads=12):
     if use_cls:
         ops.cls_merge_bwd(d_out, d_out_cls, B, T, D, M, cls_mode)
     d_qkv = torch.zeros(M + B, 3 * D, device=d, dtype=torch.bfloat16)
-    d_cls = torch.zeros(B, T, 3, D, device=d)
+    d_cls = torch.zeros(ops.spatial_bwd_scratch_floats(B, T, heads), device=d)
     ops.attn_spatial_bwd(qkv, out, out_cls if use_cls else None, d_out, d_out_cls if use_cls else None, lse, d_qkv,
-                         d_cls if use_cls else None, B, N, T, heads, use_cls, M)
+                         d_cls, B, N, T, heads, use_cls, M)
     torch.cuda.synchronize()
     xr = qkv.float().clone().requires_grad_(True)
     x = xr[:M].reshape(B, N, T, 3, heads, 64).permute(3, 0, 2, 4, 1, 5)               # (3,B,T,h,N,64)
