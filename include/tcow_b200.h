@@ -1,4 +1,4 @@
-/* tcow_b200 — C ABI of the B200 (sm_100a) Seeker-forward hot path.
+/* tcow_b200 — C ABI of the B200 (sm_100a) Seeker hot path (forward, and the training step's backward).
  *
  * The reference (basilevh/tcow) is pure Python/PyTorch and has no FFI of its own; every entry point
  * below replaces the torch.nn call(s) cited beside it (paths relative to the reference tree).  A

@@ -4,9 +4,9 @@
 // the softmax state in registers (fp32, exp2 with pre-scaled logits, warp-shuffle row reductions), apply the
 // mask in-kernel and never materialise the score matrix.
 //
-// Round-1 implementation: warp-level mma.sync m16n8k16 bf16 with ldmatrix from XOR-swizzled shared memory.
-// Both kernels are bandwidth/latency-shaped (30x30 and 301x301 problems); a tcgen05/TMEM version of the
-// spatial kernel is the planned follow-up.
+// Warp-level mma.sync m16n8k16 bf16 with ldmatrix from XOR-swizzled shared memory.  The temporal kernel (30x30
+// problems, bandwidth-shaped) is the product path; the spatial kernel here is the independent mma.sync implementation
+// kept for A/B checks (TCOW_SPATIAL_IMPL=mma) — the product path is tcgen05/TMEM (attn_spatial_tc.cu).
 #include <math.h>
 #include <stdlib.h>
 

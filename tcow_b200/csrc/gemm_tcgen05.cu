@@ -101,29 +101,8 @@ __device__ __forceinline__ uint64_t gelu_erf2(float x0, float x1) {
 }
 
 // d/dx gelu_erf(x) = Phi(x) + x*phi(x) with the same erfcx polynomial: h = q(|x|) e, e = exp(-x^2/2);
-// Phi = 1-h (x >= 0) or h (x < 0); phi = e / sqrt(2 pi).  Backward of nn.GELU() (vit.py:46,56).
-__device__ __forceinline__ float dgelu_erf(float x) {
-  const float na = fmaxf(-fabsf(x), -5.75f);
-  float q = 1.740049385e-07f;
-  q = fmaf(q, na, 5.850045000e-06f);
-  q = fmaf(q, na, 8.705152140e-05f);
-  q = fmaf(q, na, 7.601087564e-04f);
-  q = fmaf(q, na, 4.371289164e-03f);
-  q = fmaf(q, na, 1.773692295e-02f);
-  q = fmaf(q, na, 5.366283283e-02f);
-  q = fmaf(q, na, 1.275363415e-01f);
-  q = fmaf(q, na, 2.482131273e-01f);
-  q = fmaf(q, na, 3.987075090e-01f);
-  q = fmaf(q, na, 4.999948144e-01f);
-  const float w = na * 0.84932180028801904f;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-w * w));
-  const float h = q * e;
-  const float Phi = x >= 0.f ? 1.f - h : h;
-  return fmaf(x * 0.3989422804014327f, e, Phi);
-}
-
-// Packed-fp32x2 form of dgelu_erf for the DGELU epilogue (two values per issue slot, one MUFU each).
+// Phi = 1-h (x >= 0) or h (x < 0); phi = e / sqrt(2 pi).  Backward of nn.GELU() (vit.py:46,56).  Packed fp32x2 (two values
+// per issue slot, one MUFU each) for the DGELU epilogue.
 __device__ __forceinline__ uint64_t dgelu_erf2(float x0, float x1) {
   const float n0 = fmaxf(-fabsf(x0), -5.75f), n1 = fmaxf(-fabsf(x1), -5.75f);
   const uint64_t na = f2_pack(n0, n1);
