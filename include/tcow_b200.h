@@ -129,6 +129,17 @@ int tcow_flag_mean(const float* low, int64_t ld_low, float* flags, int B, int N,
  * areas[img] = (|target > 0.5|, |logit > 0 & target > 0.5|, |logit > 0 or target > 0.5|) as fp32. */
 int tcow_mask_iou_areas(const float* logits, const float* target, float* areas, int images, int hw, void* stream);
 
+/* Mask-loss reductions (loss.py:19-31 tversky_loss, :164-212 my_mask_loss) over n logits / targets / optional
+ * per-pixel weights (NULL = 1), n a multiple of 4:
+ *   sums[0..4] (double) = sum w*bce_with_logits(x,y), sum p*y, sum p*(1-y), sum (1-p)*y, sum y     (p = sigmoid(x))
+ *   grad[i] = coef[0]*w*(p - y) + p*(1-p)*(coef[1]*y + coef[2])   — coef (device, fp32[3]) carries the upstream gradients
+ * workspace: tcow_mask_loss_workspace_floats() floats. */
+int64_t tcow_mask_loss_workspace_floats(void);
+int tcow_mask_loss_sums(const float* logits, const float* target, const float* weights, int64_t n, float* workspace,
+                        double* sums, void* stream);
+int tcow_mask_loss_grad(const float* logits, const float* target, const float* weights, int64_t n, const float* coef,
+                        float* grad, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training step (BASELINE configs[3]: fwd+bwd, data-parallel).  The reference gets its backward from torch.autograd
  * over the modules cited above (train.py:93-101 loss.backward(); optimizer.step()); these entry points are the

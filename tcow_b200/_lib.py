@@ -37,6 +37,9 @@ SIGNATURES = {
                            c_void_p],
     'tcow_flag_mean': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     'tcow_mask_iou_areas': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    'tcow_mask_loss_workspace_floats': [],
+    'tcow_mask_loss_sums': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    'tcow_mask_loss_grad': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     # ---- training step
     'tcow_gemm_bf16_aux': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                            c_int, c_int, c_int, c_int, c_void_p],
@@ -81,7 +84,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = (c_char_p if name == 'tcow_last_error' else
-                          c_int64 if name == 'tcow_train_workspace_floats' else c_int)
+                          c_int64 if name in ('tcow_train_workspace_floats', 'tcow_mask_loss_workspace_floats') else c_int)
         _lib = lib
     return _lib
 

@@ -197,3 +197,38 @@ def test_backward_full_size_vs_oracle_autograd(logger):
     assert abs(loss - oloss) < 5e-3
     bad, wc, wr = compare(grads, ref)
     assert not bad, f'{len(bad)} tensors out of tolerance (worst cos {wc:.5f}, rel {wr:.4f}): {bad[:8]}'
+
+
+def test_fused_mask_loss_matches_torch_restatement():
+    """tcow_b200.loss.mask_loss_terms against the reference formulas (loss.py:19-31 tversky_loss, :181-183 weighted BCE),
+    values and gradients; also the no-target branch (loss.py:20)."""
+    from tcow_b200 import loss as tl
+    g = torch.Generator(device=DEV).manual_seed(5)
+    shape = (2, 3, 3, 4, 32, 48)
+    x = (torch.randn(shape, device=DEV, generator=g) * 3).requires_grad_(True)
+    y = (torch.rand(shape, device=DEV, generator=g) > 0.8).float()
+    w = torch.rand(shape, device=DEV, generator=g) * 2
+
+    def ref(x, y, w):
+        bce = (torch.nn.functional.binary_cross_entropy_with_logits(x, y, reduction='none') * w).mean()
+        if y.mean() >= 1e-6:
+            p = torch.sigmoid(x)
+            num = (p * y).sum()
+            den = num + 1.0 * (p * (1 - y)).sum() + 1.0 * ((1 - p) * y).sum()
+            tv = 1.0 - num / (den + 0.1)
+        else:
+            tv = torch.tensor(0.0, device=x.device)
+        return bce, tv
+
+    for yy, ww in ((y, w), (y, None), (torch.zeros_like(y), w)):
+        x.grad = None
+        b1, t1 = tl.mask_loss_terms(x, yy, ww)
+        (0.7 * b1 + 1.3 * t1).backward()
+        g1 = x.grad.clone()
+        x.grad = None
+        b2, t2 = ref(x, yy, ww if ww is not None else torch.ones_like(x))
+        (0.7 * b2 + 1.3 * t2).backward()
+        assert abs(b1.item() - b2.item()) <= 1e-5 * max(1.0, abs(b2.item()))
+        assert abs(t1.item() - t2.item()) <= 1e-5
+        assert (g1 - x.grad).abs().max().item() <= 2e-6 * max(1.0, x.grad.abs().max().item() * 1e3)
+        assert ((g1 - x.grad).norm() / x.grad.norm()).item() <= 1e-4
