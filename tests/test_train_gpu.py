@@ -232,3 +232,28 @@ def test_fused_mask_loss_matches_torch_restatement():
         assert abs(t1.item() - t2.item()) <= 1e-5
         assert (g1 - x.grad).abs().max().item() <= 2e-6 * max(1.0, x.grad.abs().max().item() * 1e3)
         assert ((g1 - x.grad).norm() / x.grad.norm()).item() <= 1e-4
+
+
+@pytest.mark.parametrize('cfg', [dict(T=1, Hf=32, Wf=32, samples=[9], causal=1),
+                                 dict(T=3, Hf=16, Wf=48, samples=[4], causal=0, flag_channels=0, track_map_resize='nearest'),
+                                 dict(T=7, Hf=48, Wf=16, samples=[1, 2, 3], causal=-1)],
+                         ids=['single_frame', 'no_flags_nearest', 'no_cls_three_samples'])
+def test_backward_edge_configs_vs_oracle_autograd(cfg, logger):
+    """Edge shapes of the training step (one frame, one patch row, no flag head, no cls token) against the oracle autograd."""
+    T, Hf, Wf = cfg['T'], cfg['Hf'], cfg['Wf']
+    fc = cfg.get('flag_channels', 3)
+    meta = dict(cfg, weight_seed=901, flag_channels=fc,
+                ref_kwargs=dict(num_total_frames=T, num_visible_frames=T, frame_height=Hf, frame_width=Wf,
+                                tracker_pretrained=False, attention_type='divided_space_time', patch_size=16,
+                                causal_attention=cfg['causal'], norm_embeddings=False, drop_path_rate=0.0, network_depth=12,
+                                track_map_stride=4, track_map_resize=cfg.get('track_map_resize', 'bilinear'),
+                                query_channels=1, output_channels=3, flag_channels=fc))
+    net = build(logger, meta)
+    rgb, q = synth.make_batch(cfg['samples'], num_frames=T, frame_height=Hf, frame_width=Wf)
+    tm, tf = synth.make_targets(cfg['samples'], num_frames=T, frame_height=Hf, frame_width=Wf, flag_channels=fc)
+    loss, grads, _ = our_grads(net, rgb, q, tm, tf)
+    sd = cached_state_dict(901, T, Hf, Wf, fc)
+    oloss, ref = mgg.oracle_grads(sd, meta, rgb, q, tm, tf)
+    assert abs(loss - oloss) < 5e-3
+    bad, wc, wr = compare(grads, ref)
+    assert not bad, f'{len(bad)} tensors out of tolerance (worst cos {wc:.5f}, rel {wr:.4f}): {bad[:8]}'
