@@ -323,7 +323,8 @@ def run_train(args):
     net.load_state_dict(synth.make_state_dict(901, num_frames=T, frame_height=HF, frame_width=WF))
     net = net.to(dev).train()
     ddp.broadcast_parameters(net)
-    sync = ddp.attach(net) if world > 1 else None
+    grad_group = ddp.make_gradient_group(args.nccl_ctas) if (world > 1 and args.nccl_ctas > 0) else None
+    sync = ddp.attach(net, process_group=grad_group) if world > 1 else None
     if sync is not None:
         sync.timing = True
     eng = net.seeker.train_engine()
@@ -516,6 +517,117 @@ def run_sweep_bench(args):
         dist.destroy_process_group()
 
 
+def run_hires(args):
+    """--workload hires (BASELINE configs[4]): T=60, 480x640 (1200 patches per frame), non-causal temporal attention (cls
+    mean path), bf16, one clip per pass and GPU; N > 1: independent replicas, no collective."""
+    import torch
+    import torch.distributed as dist
+
+    import tcow_b200
+    from tcow_b200 import synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    peaks = load_peaks()
+    Th, Hh, Wh = 60, 480, 640
+    kw = dict(SEEKER_KW, num_total_frames=Th, num_visible_frames=Th, frame_height=Hh, frame_width=Wh, causal_attention=0)
+    net = tcow_b200.Seeker(logging.getLogger('bench'), **kw)
+    net.load_state_dict(synth.make_state_dict(901, num_frames=Th, frame_height=Hh, frame_width=Wh))
+    net = net.to(dev).eval()
+    rgb_h, q_h = synth.make_batch([rank], num_frames=Th, frame_height=Hh, frame_width=Wh)
+    rgb_h, q_h = rgb_h.pin_memory(), q_h.pin_memory()
+    flop = 20878.31e9          # SURVEY.md §8d: equals FlopCounterMode on the reference
+    eng = net.seeker.engine()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        rgb, q = rgb_h.to(dev), q_h.to(dev)
+        for _ in range(args.warmup):
+            net(rgb, q)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launches = 0
+        for _ in range(args.steps):
+            net(rgb, q)
+            launches += eng.launches
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        # end to end: the clip starts in pinned host memory every step (copy stream, double-buffered: clip i+1 uploads
+        # while clip i computes); flags + per-frame mask areas are read back every step
+        copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream()
+        bufs = [(torch.empty_like(rgb), torch.empty_like(q)) for _ in range(2)]
+        ev_ready = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        res_f = torch.empty((1, Th, 3), dtype=torch.float32).pin_memory()
+        res_a = torch.empty((1, 3, Th), dtype=torch.float32).pin_memory()
+
+        def upload(i):
+            k = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[k])
+                bufs[k][0].copy_(rgb_h, non_blocking=True)
+                bufs[k][1].copy_(q_h, non_blocking=True)
+                ev_ready[k].record(copy_stream)
+
+        for k in range(2):
+            ev_free[k].record(cur)
+        upload(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                upload(i + 1)
+            k = i & 1
+            cur.wait_event(ev_ready[k])
+            mask, flags = net(bufs[k][0], bufs[k][1])
+            ev_free[k].record(cur)
+            res_f.copy_(flags, non_blocking=True)
+            res_a.copy_((mask > 0).float().mean(dim=(3, 4)), non_blocking=True)
+            cur.synchronize()
+        barrier()
+        e2e_ms = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        value = world * args.steps / (ms * 1e-3)
+        tfl = value / world * flop / 1e12
+        print(json.dumps({
+            'metric': 'seeker_fwd_clips_per_s_hires', 'value': value, 'unit': 'clips/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'TCOW Seeker forward, T=60 480x640 (S=1201 tokens per frame, 72 000 per clip), causal_attention=0, '
+                                   'batch 1 clip per GPU (BASELINE configs[4])', 'batch_per_gpu': 1,
+                       'parallelism': f'replicas x{world}, no collective', 'l2': 'activation working set ~1.2 GB >> 126 MB L2'},
+            'roofline': {'bound': 'tensor', 'achieved': round(tfl, 1), 'peak': peaks['burst'], 'unit': 'TFLOP/s',
+                         'frac': round(tfl / peaks['burst'], 4), 'traffic': None,
+                         'kernel': 'whole step, algorithmic FLOPs of the reference forward (20 878 GFLOP per clip)'},
+            'clocks': clocks,
+            'e2e': {'value': world * args.steps / (e2e_ms * 1e-3), 'unit': 'clips/s',
+                    'h2d_bytes_per_step': int(rgb_h.numel() * 4 + q_h.numel() * 4),
+                    'd2h_bytes_per_step': int((3 * Th + Th * 3) * 4)},
+            'gpu_launches': launches}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -525,12 +637,14 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunk', type=int, default=0, help='clips per engine pass (0 = engine default)')
-    ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'sweep'],
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'sweep', 'hires'],
                     help='infer = BASELINE configs[1] (the headline metric, default); train = configs[3] (fwd+bwd+AdamW, DDP); '
-                         'sweep = configs[2] (clip-sharded evaluation sweep)')
+                         'sweep = configs[2] (clip-sharded evaluation sweep); hires = configs[4] (T=60, 480x640)')
     ap.add_argument('--videos-total', type=int, default=8, help='sweep: videos in the whole sweep (fixed as GPUs grow)')
     ap.add_argument('--videos', type=int, default=2, help='train: videos per GPU (x3 queries each)')
     ap.add_argument('--drop-path', type=float, default=0.1, help='train: stochastic-depth rate (args.py default 0.1)')
+    ap.add_argument('--nccl-ctas', type=int, default=0,
+                    help='train: cap on the SMs the gradient all-reduce may occupy (0 = NCCL default, which measured faster)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     if args.impl == 'reference':
@@ -539,6 +653,8 @@ def main():
         run_train(args)
     elif args.workload == 'sweep':
         run_sweep_bench(args)
+    elif args.workload == 'hires':
+        run_hires(args)
     else:
         run_ours(args)
 

@@ -102,6 +102,24 @@ class GradSync:
         return e0.elapsed_time(e1)
 
 
+def make_gradient_group(max_ctas=4):
+    """A dedicated NCCL communicator for the gradient exchange that occupies at most `max_ctas` SMs.  The step needs about
+    8 GB/s of all-reduce bandwidth (458 MB per ~60 ms), a small fraction of NVLink; NCCL's default channel count would take
+    dozens of SMs away from the persistent one-CTA-per-SM GEMM kernels the exchange overlaps with (their tiles on the
+    occupied SMs then finish a full tile late).  Falls back to the default group when the option is unavailable.
+    MEASURED (8 x B200, bench.py --workload train): max_ctas=4 is SLOWER than NCCL's default (676 vs 728 samples/s: the
+    throttled all-reduce no longer hides behind the backward, 1.7 ms exposed) — kept as an option, not the default."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != 'nccl':
+        return None
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(max_ctas)
+        opts.config.min_ctas = 1
+        return dist.new_group(backend='nccl', pg_options=opts)
+    except (AttributeError, TypeError, RuntimeError):
+        return None
+
+
 def attach(seeker_module, process_group=None, average=True, bucket_bytes=25 << 20):
     """Make `seeker_module` (tcow_b200.Seeker or QueryMaskTracker) average its gradients over the process group
     inside its own backward.  Parameters must already be identical on every rank (broadcast_parameters)."""
