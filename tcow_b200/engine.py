@@ -65,7 +65,9 @@ class SeekerEngine:
     # ------------------------------------------------------------------ weights
     @staticmethod
     def _stamp(mod):
-        return tuple((p.data_ptr(), p._version) for p in mod.parameters())
+        # walk the modules' own tensors rather than parameters(): nn.DataParallel replicas (train.py:223) hold plain
+        # tensors in _parameters and report no parameters(), and a stale stamp would mean stale packed weights
+        return tuple((p.data_ptr(), p._version) for m in mod.modules() for p in m._parameters.values() if p is not None)
 
     def _pack(self, mod, device):
         bb = mod.tracker_backbone.timesformer.model
