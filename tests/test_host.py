@@ -129,6 +129,7 @@ def test_head_fold_equals_pool_then_linear(net):
 
 
 def test_merged_temporal_projection_is_algebraically_exact(net):
+    torch.manual_seed(1)
     mod = net.seeker
     blk = mod.tracker_backbone.timesformer.model.blocks[3]
     with torch.no_grad():
@@ -141,7 +142,7 @@ def test_merged_temporal_projection_is_algebraically_exact(net):
     b = blk.temporal_fc.weight.double() @ blk.temporal_attn.proj.bias.double() + blk.temporal_fc.bias.double()
     assert (F.linear(o, W, b) - ref).abs().max() < 1e-12
     pk = SeekerEngine(mod)._pack(mod, torch.device('cpu'))
-    assert (pk.blocks[3].t_out[0].double() - W).abs().max() < 2e-4       # one bf16 rounding of |W| ~ 0.02
+    assert (pk.blocks[3].t_out[0].double() - W).abs().max() <= 2.0 ** -8 * W.abs().max()   # one bf16 rounding
 
 
 def test_checkpoint_round_trip_in_reference_format(tmp_path, logger):
