@@ -272,10 +272,10 @@ def run_ours(args):
         'roofline': {'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
                      'frac': round(achieved / peaks['sustained'], 4),
                      # dram__bytes_read+write per launch, launch-weighted mean over the step's GEMM classes, from the
-                     # `ncu --set full` capture summarised in profiles/r01b_ncu_full.txt (B=8; bytes: qkv 392e6 x24,
+                     # `ncu --set full` capture summarised in profiles/r01e_ncu_full.txt (B=8; bytes: qkv 392e6 x24,
                      # fc1 502e6 x12, fc2 860e6 x12, proj 497e6 x24); algorithmic mean 583e6 — no operand re-reads
                      'traffic': 523.3e6 if B == 8 else None, 'traffic_unit': 'bytes/launch',
-                     'traffic_source': 'profiles/r01b_ncu_full.txt',
+                     'traffic_source': 'profiles/r01e_ncu_full.txt',
                      'kernel': 'gemm_bf16_tn_kernel (tcgen05), all launches of the step',
                      'launches_per_step': gemm_n // args.steps, 'gemm_ms_per_step': round(gemm_ms / args.steps, 3),
                      'peak_source': peaks['source'] + ' bf16_tflops_sustained (kernel timed inside a long step)',
