@@ -306,13 +306,16 @@ class SeekerEngine:
                 G('gemm_qkv', A[:M], w.t_qkv[0], w.t_qkv[1], QKV[:M], EPI_BF16)
                 L('attn_temporal', ops.attn_temporal, QKV, O, Bc * N, T, HEADS, causal_diag,
                   flops=4.0 * Bc * N * HEADS * T * T * 64, nbytes=8.0 * M * D)
+            # norm1 for the spatial branch; the cls rows enter the spatial attention through norm1 too (vit.py:180-186):
+            # they follow the patch rows in X, so the stand-alone LayerNorm covers them in the same launch
+            n1_rows = R if (use_cls and not fuse_ln) else M
             if w.t_out is not None:
-                residual('gemm_proj', O[:M], w.t_out, M, w.n1, M)                 # + norm1 for the spatial branch
+                residual('gemm_proj', O[:M], w.t_out, M, w.n1, n1_rows)
             else:
                 tmp = H[:M, :D]                                                    # H is idle here
                 G('gemm_proj', O[:M], w.t_proj[0], w.t_proj[1], tmp, EPI_BF16)
-                residual('gemm_proj', tmp, w.t_fc, M, w.n1, M)
-            if use_cls:   # the cls rows enter the spatial attention through norm1 too (vit.py:180-186)
+                residual('gemm_proj', tmp, w.t_fc, M, w.n1, n1_rows)
+            if use_cls and n1_rows == M:
                 L('ln', ops.layernorm, X[M:R], w.n1[0], w.n1[1], A[M:R], nbytes=ln_bytes(Bc))
             # spatial attention + residual (vit.py:179-215); cls is key/query 0 of every frame
             G('gemm_qkv', A[:Rs], w.s_qkv[0], w.s_qkv[1], QKV[:Rs], EPI_BF16)
