@@ -120,3 +120,109 @@ def test_two_rank_gloo_bucketed_gradient_allreduce():
     for rank, ok, tiles, nranges, same in res:
         assert ok and tiles and same
         assert nranges >= 2          # more than one bucket: the exchange overlaps the backward
+
+
+def _small_tracker(logger, causal=1, drop_path_rate=0.3):
+    import tcow_b200
+    T, Hf, Wf = 4, 32, 48
+    net = tcow_b200.Seeker(logger, num_total_frames=T, num_visible_frames=T, frame_height=Hf, frame_width=Wf,
+                           tracker_pretrained=False, causal_attention=causal, patch_size=16, drop_path_rate=drop_path_rate)
+    net.load_state_dict(cached_state_dict(901, T, Hf, Wf))
+    return net.seeker
+
+
+def test_unpack_is_the_adjoint_of_the_weight_packing(logger):
+    """The packed->reference gradient mapping (_unpack: un-merge of temporal_fc o proj, un-fold of the pooled head, conv
+    bias / cls / pos_embed bookkeeping) against torch.autograd through the same packing written as a differentiable
+    function, on the CPU."""
+    from tcow_b200.train_engine import SeekerTrainEngine
+    mod = _small_tracker(logger)
+    eng = SeekerTrainEngine(mod)
+    pk = eng._pack(mod, torch.device('cpu'))
+    bb = mod.tracker_backbone.timesformer.model
+    D, N, T, P = 768, 6, 4, 16
+    lay = _GradLayout(len(pk.blocks), D, 4 * P * P, N + 1, T, pk.n_pad, True)
+    g = torch.Generator().manual_seed(4)
+    flat = torch.randn(lay.total, generator=g)
+    # head rows past the used ones never receive gradient in a real backward
+    n_used = 3 * 16 + 3
+    lay.view(flat, 'head_w')[n_used:] = 0
+    lay.view(flat, 'head_b')[n_used:] = 0
+    dropped = [i % 2 == 1 for i in range(len(pk.blocks))]          # odd blocks: stochastic depth active (two bias gradients)
+    got = eng._unpack(mod, pk, lay, flat, True, dropped)
+
+    params = {n: p.detach().clone().double().requires_grad_(True) for n, p in mod.named_parameters()}
+    pre = 'tracker_backbone.timesformer.model.'
+    total = 0.0
+    gv = lambda name: lay.view(flat, name).double()
+    for i in range(len(pk.blocks)):
+        q = pre + f'blocks.{i}.'
+        Wp, bp = params[q + 'temporal_attn.proj.weight'], params[q + 'temporal_attn.proj.bias']
+        Wf, bf = params[q + 'temporal_fc.weight'], params[q + 'temporal_fc.bias']
+        total = total + (gv(f'b{i}.t_out_w') * (Wf @ Wp)).sum() + (gv(f'b{i}.t_out_b') * (Wf @ bp)).sum()
+        total = total + ((gv(f'b{i}.t_out_b2') if dropped[i] else gv(f'b{i}.t_out_b')) * bf).sum()
+        for ours, theirs in (('t_qkv', 'temporal_attn.qkv'), ('fc2', 'mlp.fc2'), ('n1', 'norm1')):
+            w_slot, b_slot = (ours + '_g', ours + '_b') if ours == 'n1' else (ours + '_w', ours + '_b')
+            total = total + (gv(f'b{i}.{w_slot}') * params[q + theirs + '.weight']).sum()
+            total = total + (gv(f'b{i}.{b_slot}') * params[q + theirs + '.bias']).sum()
+    Wt, bt = params['tracker_post_linear.weight'], params['tracker_post_linear.bias']
+    Wpool = Wt.reshape(3, 4, 4, 4, 4, D).mean((2, 4)).reshape(48, D)
+    bpool = bt.reshape(3, 4, 4, 4, 4).mean((2, 4)).reshape(48)
+    total = total + (gv('head_w')[:48] * Wpool).sum() + (gv('head_b')[:48] * bpool).sum()
+    total = total + (gv('head_w')[48:51] * params['flag_post_linear.weight']).sum()
+    total = total + (gv('head_b')[48:51] * params['flag_post_linear.bias']).sum()
+    # embeddings: X[(b,n,t)] = conv + conv_bias + pos[1+n] + time[t]; X[M+b] = cls + pos[0]  (B = 1 here)
+    total = total + (gv('patch_w') * params[pre + 'patch_embed.proj.weight'].reshape(D, -1)).sum()
+    total = total + (gv('time').sum(0) * params[pre + 'patch_embed.proj.bias']).sum()
+    total = total + (gv('pos') * params[pre + 'pos_embed'][0]).sum() + (gv('time') * params[pre + 'time_embed'][0]).sum()
+    total = total + (gv('pos')[0] * params[pre + 'cls_token'][0, 0]).sum()
+    total.backward()
+    checked = 0
+    for name, p in params.items():
+        if p.grad is None:
+            continue
+        ref = p.grad.float()
+        rel = ((got[name].float() - ref).norm() / ref.norm().clamp_min(1e-20)).item()
+        assert got[name].shape == ref.shape and rel < 1e-5, (name, rel)
+        checked += 1
+    assert checked >= 12 * 10 + 9
+
+
+@pytest.mark.parametrize('causal', [1, 0, 3])
+def test_drop_path_row_scales_follow_the_reference_granularity(causal, logger):
+    """Stochastic depth draws one Bernoulli per (b h w) sequence / (b t) frame / sample b (vit.py:170-172, 181-186, 216;
+    vit_utils.py:139-164) and the cls rows follow vit.py:191-198."""
+    from tcow_b200.train_engine import SeekerTrainEngine
+    mod = _small_tracker(logger, causal=causal).train()
+    eng = SeekerTrainEngine(mod)
+    B, N, T = 2, 6, 4
+    M, use_cls = B * N * T, causal in (0, 1)
+    R = M + B
+    Rs = R if use_cls else M
+    keep = 0.75
+    ov = [None] + [dict(keep=keep, t=(torch.arange(B * N) % 3 != 0).float(), s=(torch.arange(B * T) % 2 == 0).float(),
+                        m=torch.tensor([1.0, 0.0])) for _ in range(11)]
+    eng.drop_path_override = ov
+    sc = eng._drop_path_scales(mod, 12, B, N, T, M, R, Rs, use_cls, causal, torch.device('cpu'))
+    assert sc[0] is None
+    d = sc[5]
+    rows = torch.arange(M)
+    b, n, t = rows // (N * T), (rows // T) % N, rows % T
+    assert torch.equal(d['rs_t'], ov[5]['t'][b * N + n] / keep)                     # temporal: per (b, n) sequence
+    assert torch.equal(d['rs_s'][:M], ov[5]['s'][b * T + t] / keep)                  # spatial: per (b, t) frame
+    assert torch.equal(d['rs_m'][:M], ov[5]['m'][b] / keep) and torch.equal(d['rs_m'][M:], ov[5]['m'] / keep)
+    if causal == 1:      # cls residual = frame 0's output only
+        assert torch.equal(d['rs_s'][M:], ov[5]['s'].view(B, T)[:, 0] / keep) and torch.equal(d['bs_s'], d['rs_s'])
+    elif causal == 0:    # mean over frames taken after DropPath: the matmul part is pre-weighted, the bias sees the mean scale
+        assert torch.equal(d['rs_s'][M:], torch.ones(B))
+        assert torch.allclose(d['bs_s'][M:], (ov[5]['s'] / keep).view(B, T).mean(1))
+    else:
+        assert d['rs_s'].numel() == M
+    # drawn masks: block i keeps with probability 1 - linspace(0, rate, 12)[i]
+    eng.drop_path_override = None
+    torch.manual_seed(0)
+    drawn = eng._drop_path_scales(mod, 12, 64, N, T, 64 * N * T, 64 * N * T + 64, 64 * N * T + 64, True, 1, torch.device('cpu'))
+    assert drawn[0] is None
+    frac_kept = (drawn[11]['rs_t'] > 0).float().mean().item()
+    vals = drawn[11]['rs_t'].unique()
+    assert abs(frac_kept - 0.7) < 0.08 and all(min(abs(v), abs(v - 1.0 / 0.7)) < 1e-5 for v in vals.tolist())
