@@ -1,4 +1,4 @@
-# Builds the C-ABI shared library of the hot path (sm_100a only) and the oracle has no native part.
+# Builds the C-ABI shared library of the hot path (sm_100a only); the oracle is pure PyTorch and has no native part.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v
@@ -8,7 +8,9 @@ LIB := tcow_b200/libtcow_b200.so
 
 all: $(LIB)
 
-build/%.o: tcow_b200/csrc/%.cu tcow_b200/csrc/ptx.cuh tcow_b200/csrc/tcow_internal.h include/tcow_b200.h
+HDR := $(wildcard tcow_b200/csrc/*.cuh) $(wildcard tcow_b200/csrc/*.h) include/tcow_b200.h
+
+build/%.o: tcow_b200/csrc/%.cu $(HDR)
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

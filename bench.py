@@ -482,7 +482,7 @@ def run_sweep_bench(args):
         m[20 + 30 * q:60 + 30 * q, 40 + 50 * q:100 + 50 * q] = 1
         return m
 
-    fn = lambda its: sweep.run_sweep(net, its, videos.__getitem__, get_query, lambda v, q: tgt, T, dev, clips_per_pass=2)
+    fn = lambda its: sweep.run_sweep(net, its, videos.__getitem__, get_query, lambda v, q: tgt, T, dev, clips_per_pass=args.clips_per_pass)
     fn(mine[:8])                                                   # warm-up (weights packed, graphs captured)
     if world > 1:
         dist.barrier()
@@ -640,6 +640,7 @@ def main():
     ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'sweep', 'hires'],
                     help='infer = BASELINE configs[1] (the headline metric, default); train = configs[3] (fwd+bwd+AdamW, DDP); '
                          'sweep = configs[2] (clip-sharded evaluation sweep); hires = configs[4] (T=60, 480x640)')
+    ap.add_argument('--clips-per-pass', type=int, default=2, help='sweep: clips (x4 queries) per forward_queries call')
     ap.add_argument('--videos-total', type=int, default=8, help='sweep: videos in the whole sweep (fixed as GPUs grow)')
     ap.add_argument('--videos', type=int, default=2, help='train: videos per GPU (x3 queries each)')
     ap.add_argument('--drop-path', type=float, default=0.1, help='train: stochastic-depth rate (args.py default 0.1)')
