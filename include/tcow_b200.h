@@ -183,6 +183,12 @@ int tcow_layernorm_bf16_train(const float* x, const float* gamma, const float* b
 int tcow_layernorm_bwd(const void* dy, const void* xhat, const float* rstd, const float* gamma, float* G, void* Gb,
                        float* dgamma, float* dbeta, float* workspace, int rows, int D, int accumulate, void* stream);
 
+/* Same, and additionally Gs[r,:] (bf16) = next_scale[r] * G[r,:]: under stochastic depth the next branch of the backward
+ * consumes the row-scaled residual gradient (saves the separate tcow_scale_rows_bf16 pass). */
+int tcow_layernorm_bwd_scaled(const void* dy, const void* xhat, const float* rstd, const float* gamma, float* G, void* Gb,
+                              float* dgamma, float* dbeta, float* workspace, int rows, int D, int accumulate,
+                              const float* next_scale, void* Gs, void* stream);
+
 /* Bias gradient: out[N] (fp32) = (accumulate ? out : 0) + sum_r x[r, :] for x bf16 [rows, N] (pitch ldx). */
 int tcow_colsum_bf16(const void* x, int64_t ldx, int rows, int N, float* out, float* workspace, int accumulate,
                      void* stream);

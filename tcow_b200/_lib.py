@@ -52,6 +52,8 @@ SIGNATURES = {
                                   c_void_p],
     'tcow_layernorm_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_int, c_int, c_int, c_void_p],
+    'tcow_layernorm_bwd_scaled': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'tcow_colsum_bf16': [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     'tcow_embed_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     'tcow_mask_head_bwd': [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
                                                                const __nv_bfloat16* __restrict__ xhat,
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                float* __restrict__ G, __nv_bfloat16* __restrict__ Gb,
-                                                               float* __restrict__ partial, int rows, int accumulate) {
+                                                               float* __restrict__ partial, int rows, int accumulate,
+                                                               const float* __restrict__ next_scale,
+                                                               __nv_bfloat16* __restrict__ Gs) {
   constexpr int D = NV * 256;
   __shared__ float s_red[8][2][256];  // one 256-column group (vector index) at a time
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -123,6 +125,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
     }
     const float c1 = s1 * (1.0f / D), c2 = s2 * (1.0f / D);
     uint4* br = reinterpret_cast<uint4*>(Gb + static_cast<size_t>(row) * D);
+    // stochastic depth: the next branch consumes scale[row] * G as well (its dY operand) — written here instead of by a
+    // separate pass over Gb
+    uint4* sr = Gs ? reinterpret_cast<uint4*>(Gs + static_cast<size_t>(row) * D) : nullptr;
+    const float nsc = Gs ? __ldg(next_scale + row) : 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const uint32_t aw[4] = {a[v].x, a[v].y, a[v].z, a[v].w}, bw[4] = {b[v].x, b[v].y, b[v].z, b[v].w};
@@ -145,6 +151,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
       gr[(v * 32 + lane) * 2] = o0;
       gr[(v * 32 + lane) * 2 + 1] = o1;
       br[v * 32 + lane] = make_uint4(pack_bf16(o0.x, o0.y), pack_bf16(o0.z, o0.w), pack_bf16(o1.x, o1.y), pack_bf16(o1.z, o1.w));
+      if (sr)
+        sr[v * 32 + lane] = make_uint4(pack_bf16(nsc * o0.x, nsc * o0.y), pack_bf16(nsc * o0.z, nsc * o0.w),
+                                       pack_bf16(nsc * o1.x, nsc * o1.y), pack_bf16(nsc * o1.z, nsc * o1.w));
     }
   }
   // block reduction of the per-warp column sums, one 256-column group at a time
@@ -394,12 +403,14 @@ static int launch_ln_train(const float* x, const float* g, const float* b, void*
 
 template <int NV>
 static int launch_ln_bwd(const void* dy, const void* xhat, const float* rstd, const float* gamma, float* G, void* Gb,
-                         float* dgamma, float* dbeta, float* ws, int rows, int accumulate, cudaStream_t s) {
+                         float* dgamma, float* dbeta, float* ws, int rows, int accumulate, cudaStream_t s,
+                         const float* next_scale = nullptr, void* Gs = nullptr) {
   constexpr int D = NV * 256;
   int blocks = (rows + 7) / 8;
   if (blocks > LNB_MAX_BLOCKS) blocks = LNB_MAX_BLOCKS;
   layernorm_bwd_kernel<NV><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(xhat),
-                                                 rstd, gamma, G, static_cast<__nv_bfloat16*>(Gb), ws, rows, accumulate);
+                                                 rstd, gamma, G, static_cast<__nv_bfloat16*>(Gb), ws, rows, accumulate,
+                                                 next_scale, static_cast<__nv_bfloat16*>(Gs));
   int rc = check_launch("layernorm_bwd_kernel");
   if (rc) return rc;
   finalize_sum_kernel<<<(D + 31) / 32, 256, 0, s>>>(ws, blocks, 2 * D, dgamma, D, 1);
@@ -440,6 +451,20 @@ extern "C" int tcow_layernorm_bwd(const void* dy, const void* xhat, const float*
     case 1024: return launch_ln_bwd<4>(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, rows, accumulate, s);
   }
   return set_error(TCOW_ERR_ARG, "layernorm_bwd: unsupported width %d (768 or 1024)", D);
+}
+
+extern "C" int tcow_layernorm_bwd_scaled(const void* dy, const void* xhat, const float* rstd, const float* gamma, float* G,
+                                         void* Gb, float* dgamma, float* dbeta, float* workspace, int rows, int D,
+                                         int accumulate, const float* next_scale, void* Gs, void* stream) {
+  using namespace tcow;
+  if (!dy || !xhat || !rstd || !gamma || !G || !Gb || !dgamma || !dbeta || !workspace || !next_scale || !Gs || rows <= 0)
+    return set_error(TCOW_ERR_ARG, "layernorm_bwd_scaled: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (D) {
+    case 768: return launch_ln_bwd<3>(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, rows, accumulate, s, next_scale, Gs);
+    case 1024: return launch_ln_bwd<4>(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, rows, accumulate, s, next_scale, Gs);
+  }
+  return set_error(TCOW_ERR_ARG, "layernorm_bwd_scaled: unsupported width %d (768 or 1024)", D);
 }
 
 extern "C" int tcow_colsum_bf16(const void* x, int64_t ldx, int rows, int N, float* out, float* workspace,

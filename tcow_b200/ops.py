@@ -170,13 +170,22 @@ def layernorm_train(x, gamma, beta, out, xhat, rstd, eps=1e-6):
     return out
 
 
-def layernorm_bwd(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, accumulate=True):
+def layernorm_bwd(dy, xhat, rstd, gamma, G, Gb, dgamma, dbeta, workspace, accumulate=True, next_scale=None, Gs=None):
+    """next_scale / Gs: also write Gs = next_scale[:, None] * G (bf16) for the next branch under stochastic depth."""
     _chk(dy, torch.bfloat16, 'layernorm_bwd.dy'); _chk(xhat, torch.bfloat16, 'layernorm_bwd.xhat')
     _chk(G, torch.float32, 'layernorm_bwd.G'); _chk(Gb, torch.bfloat16, 'layernorm_bwd.Gb')
     rows, D = dy.shape
     for t in (dy, xhat, G, Gb):
         if not t.is_contiguous() or tuple(t.shape) != (rows, D):
             raise ValueError('layernorm_bwd: contiguous [rows, D] tensors required')
+    if next_scale is not None:
+        _chk(next_scale, torch.float32, 'layernorm_bwd.next_scale'); _chk(Gs, torch.bfloat16, 'layernorm_bwd.Gs')
+        if next_scale.numel() < rows or not Gs.is_contiguous() or tuple(Gs.shape) != (rows, D):
+            raise ValueError('layernorm_bwd: next_scale needs one entry per row and Gs the shape of G')
+        _lib.call('tcow_layernorm_bwd_scaled', dy.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                  G.data_ptr(), Gb.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), workspace.data_ptr(), rows, D,
+                  int(accumulate), next_scale.data_ptr(), Gs.data_ptr(), _stream())
+        return
     _lib.call('tcow_layernorm_bwd', dy.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), G.data_ptr(),
               Gb.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), workspace.data_ptr(), rows, D, int(accumulate),
               _stream())

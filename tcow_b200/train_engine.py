@@ -252,7 +252,9 @@ class SeekerTrainEngine:
                 else:                # the mean over frames is taken after DropPath: the matmul part is pre-weighted
                     rs_s, bs_s = torch.cat([rs_s, torch.ones(B, device=device)]), torch.cat([rs_s, ss.view(B, T).mean(1)])
             rs_m = torch.cat([sm.repeat_interleave(N * T), sm])
-            out.append(dict(rs_t=rs_t, rs_s=rs_s.contiguous(), bs_s=bs_s.contiguous(), rs_m=rs_m.contiguous(), ss=ss))
+            pad = lambda v: torch.cat([v, v.new_zeros(R - v.numel())]).contiguous() if v.numel() < R else v.contiguous()
+            out.append(dict(rs_t=rs_t, rs_s=rs_s.contiguous(), bs_s=bs_s.contiguous(), rs_m=rs_m.contiguous(), ss=ss,
+                            rs_t_pad=pad(rs_t), rs_s_pad=pad(rs_s)))
         return out
 
     # ------------------------------------------------------------------ forward (saves what backward needs)
@@ -401,9 +403,17 @@ class SeekerTrainEngine:
             def colsum(x, name):
                 L('colsum', ops.colsum, x, gv(name), ws, True, nbytes=2.0 * x.numel())
 
-            def ln_bwd(rows, xh, rs, gamma, gname, bname, accumulate=True):
-                L('ln_bwd', ops.layernorm_bwd, dA[:rows], xh, rs, gamma, G_[:rows], Gb[:rows], gv(gname), gv(bname), ws,
-                  accumulate, nbytes=(14.0 if accumulate else 10.0) * rows * D)
+            gs_tag = [None]     # which branch the row-scaled copy in sc['Gs'] currently belongs to (stochastic depth)
+
+            def ln_bwd(rows, xh, rs, gamma, gname, bname, accumulate=True, next_scale=None, tag=None):
+                # next_scale: the NEXT branch of the backward runs under DropPath: write its row-scaled dY here too
+                if next_scale is None:
+                    L('ln_bwd', ops.layernorm_bwd, dA[:rows], xh, rs, gamma, G_[:rows], Gb[:rows], gv(gname), gv(bname), ws,
+                      accumulate, nbytes=(14.0 if accumulate else 10.0) * rows * D)
+                else:
+                    L('ln_bwd', ops.layernorm_bwd, dA[:rows], xh, rs, gamma, G_[:rows], Gb[:rows], gv(gname), gv(bname), ws,
+                      accumulate, next_scale, sc['Gs'][:rows], nbytes=(16.0 if accumulate else 12.0) * rows * D)
+                    gs_tag[0] = tag
 
             # ---- mask head (mask_tracker.py:112-137) and the optional final norm (vision_tf.py:152-153)
             d_mask = d_mask.to(torch.float32).contiguous()
@@ -430,23 +440,28 @@ class SeekerTrainEngine:
                 dp = s.dp
                 Gs = Gb                 # branch gradient = residual gradient, row-scaled under stochastic depth
 
-                def scaled(rows, scale):
-                    L('scale_rows', ops.scale_rows, Gb[:rows], scale, sc['Gs'][:rows], nbytes=4.0 * rows * D)
+                def scaled(rows, scale, tag):
+                    if gs_tag[0] != tag:      # not produced by the preceding LayerNorm backward: one pass over Gb
+                        L('scale_rows', ops.scale_rows, Gb[:rows], scale, sc['Gs'][:rows], nbytes=4.0 * rows * D)
+                    gs_tag[0] = None
                     return sc['Gs']
                 # ---- MLP (vit.py:216)
                 if dp is not None:
-                    Gs = scaled(R, dp['rs_m'])
+                    Gs = scaled(R, dp['rs_m'], ('m', bi))
                 colsum(Gs, p + 'fc2_b')
                 WG('wgrad_fc2', Gs, s.H, gv(p + 'fc2_w'))
                 L('dgrad_fc2', ops.gemm_aux, Gs, w.fc2[2], None, dZ, s.Z, EPI_BF16_DGELU, flops=2.0 * R * 4 * D * D)
                 colsum(dZ, p + 'fc1_b')
                 WG('wgrad_fc1', dZ, s.A_m, gv(p + 'fc1_w'))
                 G('dgrad_fc1', dZ, w.fc1[2], None, dA, EPI_BF16)
-                ln_bwd(R, s.xh_m, s.rs_m, w.n2[0], p + 'n2_g', p + 'n2_b')
+                if dp is not None:
+                    ln_bwd(R, s.xh_m, s.rs_m, w.n2[0], p + 'n2_g', p + 'n2_b', next_scale=dp['rs_s_pad'], tag=('s', bi))
+                else:
+                    ln_bwd(R, s.xh_m, s.rs_m, w.n2[0], p + 'n2_g', p + 'n2_b')
                 # ---- spatial attention (vit.py:179-215)
                 Gs = Gb
                 if dp is not None:
-                    Gs = scaled(Rs, dp['rs_s'])
+                    Gs = scaled(Rs, dp['rs_s'], ('s', bi))
                     colsum(Gs[:M], p + 's_proj_b')
                     if use_cls:      # cls rows: the bias term carries its own scale (mean of the frame scales, causal==0)
                         gv(p + 's_proj_b').add_((dp['bs_s'][M:R, None] * Gb[M:R].float()).sum(0))
@@ -467,12 +482,15 @@ class SeekerTrainEngine:
                 colsum(dQKV[:Rs], p + 's_qkv_b')
                 WG('wgrad_qkv', dQKV[:Rs], s.A_s, gv(p + 's_qkv_w'))
                 G('dgrad_qkv', dQKV[:Rs], w.s_qkv[2], None, dA[:Rs], EPI_BF16)
-                ln_bwd(Rs, s.xh_s, s.rs_s, w.n1[0], p + 'n1_g', p + 'n1_b')
+                if dp is not None and merged:
+                    ln_bwd(Rs, s.xh_s, s.rs_s, w.n1[0], p + 'n1_g', p + 'n1_b', next_scale=dp['rs_t_pad'], tag=('t', bi))
+                else:
+                    ln_bwd(Rs, s.xh_s, s.rs_s, w.n1[0], p + 'n1_g', p + 'n1_b')
                 # ---- temporal attention + temporal_fc (vit.py:169-176)
                 if merged:
                     Gs = Gb
                     if dp is not None:
-                        Gs = scaled(M, dp['rs_t'])
+                        Gs = scaled(M, dp['rs_t'], ('t', bi))
                         colsum(Gb[:M], p + 't_out_b2')          # temporal_fc.bias sits outside DropPath
                     colsum(Gs[:M], p + 't_out_b')
                     WG('wgrad_proj', Gs[:M], s.O_t, gv(p + 't_out_w'))
@@ -489,7 +507,12 @@ class SeekerTrainEngine:
                 colsum(dQKV[:M], p + 't_qkv_b')
                 WG('wgrad_qkv', dQKV[:M], s.A_t, gv(p + 't_qkv_w'))
                 G('dgrad_qkv', dQKV[:M], w.t_qkv[2], None, dA[:M], EPI_BF16)
-                ln_bwd(M, s.xh_t, s.rs_t, w.tn1[0], p + 'tn1_g', p + 'tn1_b')
+                dp_prev = sv.blocks[bi - 1].dp if bi > 0 else None
+                if dp_prev is not None:   # the MLP branch of block bi-1 is next: its scale for the patch rows here, cls rows apart
+                    ln_bwd(M, s.xh_t, s.rs_t, w.tn1[0], p + 'tn1_g', p + 'tn1_b', next_scale=dp_prev['rs_m'], tag=('m', bi - 1))
+                    sc['Gs'][M:R].copy_((dp_prev['rs_m'][M:R, None] * Gb[M:R].float()).to(torch.bfloat16))
+                else:
+                    ln_bwd(M, s.xh_t, s.rs_t, w.tn1[0], p + 'tn1_g', p + 'tn1_b')
                 sv.blocks_dp[bi] = s
                 sv.blocks[bi] = None           # this block's activations are no longer needed
                 if sync is not None:

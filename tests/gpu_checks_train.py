@@ -133,6 +133,32 @@ def check_ln_train_bwd(rows, D=768, accumulate=True):
         f'ln_train_bwd rows={rows} acc={accumulate} (y {e_y:.2f} dx {e_dx:.2f} gb {e_gb:.2f} dgamma {e_dg:.2f} dbeta {e_db:.2f} of tol)'
 
 
+def check_ln_bwd_scaled(rows, D=768):
+    """The stochastic-depth variant also writes Gs = next_scale * G (bf16); everything else must equal the plain kernel."""
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(23)
+    x = torch.randn(rows, D, device=d, generator=g)
+    gm = 1 + 0.1 * torch.randn(D, device=d, generator=g)
+    bt = 0.1 * torch.randn(D, device=d, generator=g)
+    y, xhat, rstd = torch.empty(rows, D, device=d, dtype=torch.bfloat16), torch.empty(rows, D, device=d, dtype=torch.bfloat16), torch.empty(rows, device=d)
+    ops.layernorm_train(x, gm, bt, y, xhat, rstd)
+    dy = (torch.randn(rows, D, device=d, generator=g) * 0.1).to(torch.bfloat16)
+    G0 = torch.randn(rows, D, device=d, generator=g) * 0.1
+    sc = (torch.rand(rows, device=d, generator=g) > 0.3).float() / 0.7
+    outs = []
+    for scaled in (False, True):
+        G, Gb, Gs = G0.clone(), torch.empty_like(y), torch.full_like(y, 7.0)
+        dgm, dbt = torch.zeros(D, device=d), torch.zeros(D, device=d)
+        ops.layernorm_bwd(dy, xhat, rstd, gm, G, Gb, dgm, dbt, _ws(d), True, sc if scaled else None, Gs if scaled else None)
+        outs.append((G, Gb, Gs, dgm, dbt))
+    torch.cuda.synchronize()
+    (G1, Gb1, _, dg1, db1), (G2, Gb2, Gs2, dg2, db2) = outs
+    same = torch.equal(G1, G2) and torch.equal(Gb1, Gb2) and torch.equal(dg1, dg2) and torch.equal(db1, db2)
+    ref = (sc[:, None] * G2).to(torch.bfloat16).float()
+    err = (Gs2.float() - ref).abs().max().item()
+    return (0.0 if same else float('inf')) + err, 2.0 ** -8 * ref.abs().max().item(), f'ln_bwd_scaled rows={rows} (identical to plain: {same}, Gs err {err:.2e})'
+
+
 def check_colsum(rows, N, pad=0):
     d = _dev()
     g = torch.Generator(device=d).manual_seed(15)
@@ -283,6 +309,8 @@ TRAIN_CHECKS = [
     ('ln_train_bwd_noacc', lambda: check_ln_train_bwd(300, accumulate=False)),
     ('ln_train_bwd_1024', lambda: check_ln_train_bwd(100, 1024)),
     ('ln_train_bwd_one', lambda: check_ln_train_bwd(1)),
+    ('ln_bwd_scaled', lambda: check_ln_bwd_scaled(9001)),
+    ('ln_bwd_scaled_small', lambda: check_ln_bwd_scaled(5)),
     ('colsum', lambda: check_colsum(9001, 768)),
     ('colsum_wide', lambda: check_colsum(3000, 3072, pad=8)),
     ('colsum_64', lambda: check_colsum(5000, 64)),

@@ -1,1 +1,1 @@
-for c in 2 4 1; do python bench.py --workload sweep --clips-per-pass $c 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('clips_per_pass', $c, round(d['value'],1), round(d['ms_per_step'],1))"; done
+timeout 300 python tools/gpu_diag_train.py ln_bwd_scaled 2>&1 | tail -4 | cut -c1-170
