@@ -5,6 +5,7 @@ import socket
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
+import pytest
 
 from tcow_b200 import sweep
 
@@ -76,3 +77,50 @@ def test_two_rank_gloo_sweep():
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert n == 48 and tmax == 2.0 and complete
+
+
+def test_run_sweep_host_logic_with_a_stub_network(monkeypatch):
+    """Clip grouping, ragged query groups (padded by repeating the last query), uint8 expansion and the per-item rows of
+    run_sweep, with the network and the device kernel replaced by torch stubs (the real ones are covered on the GPU)."""
+    import torch
+
+    from tcow_b200 import ops
+    T, Hf, Wf, F = 3, 8, 12, 10
+
+    class StubNet:
+        calls = []
+
+        def forward_queries(self, rgb, q):
+            StubNet.calls.append((tuple(rgb.shape), tuple(q.shape)))
+            B, Qs = q.shape[:2]
+            # logits > 0 exactly where the query rectangle of frame 0 is, in every frame and channel
+            m = (q[:, :, :, 0:1] > 0).float().expand(B, Qs, 3, T, Hf, Wf) * 2 - 1
+            flags = rgb.mean(dim=(1, 3, 4))[:, None, :, None].expand(B, Qs, T, 3).contiguous()
+            return m.contiguous(), flags
+
+    def areas(logits, target):
+        p, g = logits > 0, target > 0.5
+        return torch.stack([g.sum((-1, -2)), (p & g).sum((-1, -2)), (p | g).sum((-1, -2))], -1).float()
+
+    monkeypatch.setattr(ops, 'mask_iou_areas', areas)
+    items = sweep.plan_sweep(num_videos=2, num_queries=3, num_video_frames=F, num_frames=T, query_idx=1)
+    items = [it for it in items if not (it.video == 1 and it.frame_stride == 2 and it.query == 2)]   # one ragged group
+    vids = {v: torch.full((3, F, Hf, Wf), 51 * (v + 1), dtype=torch.uint8) for v in range(2)}      # uint8: /255 on "device"
+
+    def get_query(v, q):
+        m = torch.zeros(Hf, Wf)
+        m[q:q + 2, 0:4] = 1
+        return m
+
+    tgt = torch.zeros(3, F, Hf, Wf)
+    tgt[0, :, 0:2, 0:4] = 1           # channel 0: identical to query 0's rectangle -> IoU 1 for q = 0
+    res = sweep.run_sweep(StubNet(), items, vids.__getitem__, get_query, lambda v, q: tgt, T, torch.device('cpu'),
+                          clips_per_pass=2)
+    assert sorted(res) == sorted((i.video, i.query, i.frame_start, i.frame_stride) for i in items)
+    n_groups = len(sweep.group_by_clip(items))
+    assert len(StubNet.calls) == (n_groups + 1) // 2 and all(c[1][1] == 3 for c in StubNet.calls)   # padded to 3 queries
+    r0 = res[(0, 0, 1, 1)]
+    assert r0['mean_snitch_iou'] == pytest.approx(1.0) and r0['count_snitch_iou'] == T
+    assert r0['count_occl_mask_iou'] == 0 and r0['mean_occl_mask_iou'] == -1.0                       # empty target channel
+    assert res[(0, 2, 1, 1)]['mean_snitch_iou'] == pytest.approx(0.0)                                 # disjoint rectangle
+    assert res[(1, 0, 1, 3)]['flag_occl_mean'] == pytest.approx(102 / 255, abs=1e-6)                 # uint8 frames expanded
