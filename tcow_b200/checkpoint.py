@@ -20,19 +20,7 @@ import numpy as np
 import torch
 
 from . import seeker as seeker_mod
-
-
-def _parse_pretrained(v):
-    """mask_tracker.py:52-67."""
-    if isinstance(v, bool):
-        return v, ''
-    if isinstance(v, str):
-        if v.lower() in ['1', 'y', 'yes', 't', 'true']:
-            return True, ''
-        if len(v) <= 5:
-            return False, ''
-        return True, v
-    raise ValueError(f'Invalid tracker_pretrained value: {v}.')
+from .mask_tracker import _parse_tracker_pretrained as _parse_pretrained
 
 
 def build_seeker(logger, seeker_args, state_dict=None, device=None):

@@ -9,6 +9,17 @@ from .engine import SeekerEngine
 from .train_engine import SeekerFunction, SeekerTrainEngine
 
 
+def _parse_tracker_pretrained(value):
+    """(use_pretrained, path) from a bool or the string forms args.py:150 allows (mask_tracker.py:52-67)."""
+    if isinstance(value, bool):
+        return value, ''
+    if not isinstance(value, str):
+        raise ValueError(f'Invalid tracker_pretrained value: {value}.')
+    if value.lower() in ('1', 'y', 'yes', 't', 'true'):
+        return True, ''
+    return (False, '') if len(value) <= 5 else (True, value)
+
+
 class QueryMaskTracker(torch.nn.Module):
 
     def __init__(self, logger, num_total_frames=24, num_visible_frames=16, frame_height=224, frame_width=288,
@@ -18,56 +29,35 @@ class QueryMaskTracker(torch.nn.Module):
                  flag_channels=3):
         super().__init__()
         self.logger = logger
-        self.num_total_frames = num_total_frames
-        self.num_visible_frames = num_visible_frames
-        self.frame_height = frame_height
-        self.frame_width = frame_width
-        self.attention_type = attention_type
-        self.patch_size = patch_size
-        self.causal_attention = causal_attention
-        self.norm_embeddings = norm_embeddings
-        self.drop_path_rate = drop_path_rate
-        self.network_depth = network_depth
-        self.track_map_stride = track_map_stride
-        self.track_map_resize = track_map_resize
-        self.query_channels = query_channels
-        self.output_channels = output_channels
-        self.flag_channels = flag_channels
-        self.input_channels = 3 + self.query_channels
-
-        # mask_tracker.py:52-69 — same parsing of the pretrained flag / path.
-        self.pretrained_path = ''
-        if isinstance(tracker_pretrained, bool):
-            self.tracker_pretrained = tracker_pretrained
-        elif isinstance(tracker_pretrained, str):
-            if tracker_pretrained.lower() in ['1', 'y', 'yes', 't', 'true']:
-                self.tracker_pretrained = True
-            elif len(tracker_pretrained) <= 5:
-                self.tracker_pretrained = False
-            else:
-                self.tracker_pretrained = True
-                self.pretrained_path = tracker_pretrained
-        else:
-            raise ValueError(f'Invalid tracker_pretrained value: {tracker_pretrained}.')
-        self.logger.info(f'(QueryMaskTracker) tracker_pretrained: {self.tracker_pretrained} '
-                         f'pretrained_path: {self.pretrained_path}')
-        if self.query_channels != 1:
+        # every constructor argument becomes an attribute of the same name, as callers of the reference expect
+        # (mask_tracker.py:30-50); tracker_pretrained is normalised to (bool, path) by the rule of mask_tracker.py:52-67
+        for name, value in dict(num_total_frames=num_total_frames, num_visible_frames=num_visible_frames,
+                                frame_height=frame_height, frame_width=frame_width, attention_type=attention_type,
+                                patch_size=patch_size, causal_attention=causal_attention,
+                                norm_embeddings=norm_embeddings, drop_path_rate=drop_path_rate,
+                                network_depth=network_depth, track_map_stride=track_map_stride,
+                                track_map_resize=track_map_resize, query_channels=query_channels,
+                                output_channels=output_channels, flag_channels=flag_channels).items():
+            setattr(self, name, value)
+        self.input_channels = 3 + query_channels
+        self.tracker_pretrained, self.pretrained_path = _parse_tracker_pretrained(tracker_pretrained)
+        logger.info(f'(QueryMaskTracker) tracker_pretrained: {self.tracker_pretrained} '
+                    f'pretrained_path: {self.pretrained_path}')
+        if query_channels != 1:
             raise NotImplementedError('tcow_b200 supports query_channels=1 (train.py:202 hard-codes it)')
+        if frame_height % patch_size or frame_width % patch_size:
+            raise AssertionError('frame size must be a multiple of the patch size (mask_tracker.py:89-90)')
 
         self.tracker_backbone = vision_tf.MyDenseTimeSformerBackbone(
-            self.logger, num_frames=self.num_total_frames, frame_height=self.frame_height,
-            frame_width=self.frame_width, patch_dim=self.patch_size, in_channels=self.input_channels,
-            pretrained=self.tracker_pretrained, pretrained_path=self.pretrained_path,
-            attention_type=self.attention_type, causal_attention=self.causal_attention,
-            norm_embeddings=self.norm_embeddings, drop_path_rate=self.drop_path_rate,
-            network_depth=self.network_depth)
+            logger, num_frames=num_total_frames, frame_height=frame_height, frame_width=frame_width,
+            patch_dim=patch_size, in_channels=self.input_channels, pretrained=self.tracker_pretrained,
+            pretrained_path=self.pretrained_path, attention_type=attention_type, causal_attention=causal_attention,
+            norm_embeddings=norm_embeddings, drop_path_rate=drop_path_rate, network_depth=network_depth)
         self.use_feature_dim = self.tracker_backbone.output_feature_dim
-        self.tracker_post_linear = torch.nn.Linear(
-            self.use_feature_dim, self.output_channels * self.patch_size * self.patch_size)
-        if self.flag_channels > 0:
-            self.flag_post_linear = torch.nn.Linear(self.use_feature_dim, self.flag_channels)
-        assert self.frame_height % self.patch_size == 0
-        assert self.frame_width % self.patch_size == 0
+        # parameter names below are part of the checkpoint contract (251-tensor state dict)
+        self.tracker_post_linear = torch.nn.Linear(self.use_feature_dim, output_channels * patch_size * patch_size)
+        if flag_channels > 0:
+            self.flag_post_linear = torch.nn.Linear(self.use_feature_dim, flag_channels)
         self._engine = None  # built lazily on the parameters' device; not part of the state dict
         self._train_engine = None
 
