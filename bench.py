@@ -3,6 +3,7 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
   python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+  python bench.py --impl eager --steps K --warmup W        # the reference algorithm under stock eager PyTorch on the GPU
 
 Metric (BASELINE.json): Seeker fwd clips/s at T=30, 240x320 — one "clip" = one (video clip, query) sample
 through Seeker.forward (model/seeker.py:24).  Workload: configs[1] — batch 8 synthetic clips per GPU, bf16
@@ -90,6 +91,116 @@ class ClockSampler:
                 'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def dist_env():
+    """(world, rank, local, device) of this process; NCCL process group when launched by torchrun."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=dev)
+    return world, rank, local, dev
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world, dev):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def mask_iou(a, b):
+    a, b = a > 0, b > 0                                     # eval/metrics.py:18
+    union = (a | b).sum().item()
+    return 1.0 if union == 0 else (a & b).sum().item() / union
+
+
+def e2e_measure(net, rgb_h, q_h, frame_scale, steps, warm, world, dev):
+    """The metric through the module's own forward with HOST buffers: every step the inputs are copied from pinned host
+    memory (copy stream, double-buffered: step i+1 uploads while step i computes) and the step's full result — the
+    (B,3,T,Hf,Wf) fp32 logits Seeker.forward returns plus the flags, what eval/inference.py:91 moves to the host — is
+    copied back to pinned host memory on a second copy stream (double-buffered: step i's logits travel while step i+1
+    computes; the host waits for result i-1 before it enqueues step i+1).  Returns (ms per step, h2d bytes, d2h bytes)."""
+    import torch
+    cur = torch.cuda.current_stream()
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty(rgb_h.shape, dtype=rgb_h.dtype, device=dev), torch.empty(q_h.shape, dtype=q_h.dtype, device=dev))
+            for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    out_h = []
+
+    def upload(i):
+        k = i & 1
+        with torch.cuda.stream(up):
+            up.wait_event(ev_free[k])
+            bufs[k][0].copy_(rgb_h, non_blocking=True)
+            bufs[k][1].copy_(q_h, non_blocking=True)
+            ev_ready[k].record(up)
+
+    def run(n):
+        for k in range(2):
+            ev_free[k].record(cur)
+        upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            k = i & 1
+            cur.wait_event(ev_ready[k])
+            mask, flags = net(bufs[k][0], bufs[k][1], frame_scale=frame_scale)
+            ev_free[k].record(cur)
+            done = torch.cuda.Event()
+            done.record(cur)
+            if not out_h:
+                for _ in range(2):
+                    out_h.append((torch.empty(mask.shape, dtype=mask.dtype).pin_memory(),
+                                  torch.empty(flags.shape, dtype=flags.dtype).pin_memory()))
+            with torch.cuda.stream(down):
+                down.wait_event(done)
+                out_h[k][0].copy_(mask, non_blocking=True)
+                out_h[k][1].copy_(flags, non_blocking=True)
+                mask.record_stream(down)
+                flags.record_stream(down)
+                ev_out[k].record(down)
+            if i >= 1:
+                ev_out[k ^ 1].synchronize()          # result i-1 has arrived in host memory
+        ev_out[(n - 1) & 1].synchronize()
+
+    with torch.no_grad():
+        run(max(min(warm, 3), 2))
+        barrier(world)
+        t0 = time.perf_counter()
+        run(steps)
+        barrier(world)
+        ms = max_over_ranks(1e3 * (time.perf_counter() - t0), world, dev)
+    h2d = int(rgb_h.numel() * rgb_h.element_size() + q_h.numel() * q_h.element_size())
+    d2h = int(sum(t.numel() * t.element_size() for t in out_h[0]))
+    return ms / steps, h2d, d2h, out_h[(steps - 1) & 1]
+
+
+def load_traffic():
+    """DRAM bytes per launch per kernel class, written by tools/ncu_traffic.py from an ncu capture of this bench."""
+    p = os.path.join(ROOT, 'profiles', 'kernel_traffic.json')
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p))
+
+
 def cpu_forward_timing(n_forwards, threads):
     """The reference algorithm on the host cores: the oracle restatement (fp32, torch CPU), B=1 per forward."""
     import torch
@@ -130,6 +241,74 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def eager_gpu_baseline(dev, rgb_d, q_d, ours_mask, steps, warm):
+    """SURVEY §8(d) last row: the reference algorithm (the oracle restatement of model/seeker.py:24 — the reference tree
+    itself does not exist on the GPU box) under stock eager PyTorch on the same B200, same weights and clips: fp32 with
+    TF32 off (oracle grade) and torch.autocast('cuda', bfloat16) (cuBLAS/cuDNN/ATen bf16 — "the code to beat").  A
+    reported baseline; nothing of it is on the product path."""
+    import torch
+    from oracle import seeker_oracle
+    from tcow_b200 import synth
+    sd = {k: v.to(dev) for k, v in synth.make_state_dict(901, num_frames=T, frame_height=HF, frame_width=WF).items()}
+    B = rgb_d.shape[0]
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out = {'kind': 'port', 'what': 'oracle/seeker_oracle.py (op-by-op restatement of the reference forward) on cuda, stock '
+                                   f'eager PyTorch {torch.__version__}, batch {B}, same weights and clips'}
+
+    def timed(fn, n_warm, n):
+        for _ in range(n_warm):
+            r = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return r, e0.elapsed_time(e1) / n
+
+    try:
+        with torch.no_grad():
+            (m32, f32), ms32 = timed(lambda: seeker_oracle.seeker_forward(sd, rgb_d, q_d, causal_attention=1), 1, max(2, steps // 4))
+
+            def bf():
+                with torch.autocast('cuda', dtype=torch.bfloat16):
+                    return seeker_oracle.seeker_forward(sd, rgb_d, q_d, causal_attention=1)
+            (m16, f16), ms16 = timed(bf, max(2, warm // 2), max(3, steps // 2))
+        m16 = m16.float()
+        out['fp32_tf32_off'] = {'clips_per_s': B / (ms32 * 1e-3), 'ms_per_step': ms32}
+        out['autocast_bf16'] = {'clips_per_s': B / (ms16 * 1e-3), 'ms_per_step': ms16,
+                                'max_dlogit_vs_fp32': (m16 - m32).abs().max().item(),
+                                'min_iou_vs_fp32': min(mask_iou(m16[b], m32[b]) for b in range(B))}
+        out['ours_vs_fp32_eager'] = {'max_dlogit': (ours_mask - m32).abs().max().item(),
+                                     'min_iou': min(mask_iou(ours_mask[b], m32[b]) for b in range(B))}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
+def golden_parity(mask, flags):
+    """Clips 0 and 7 of the batch this bench times (rank 0) against the UNMODIFIED reference's outputs on the same
+    clips (tests/golden/full_bench_b8.npz, made by oracle/make_golden.py).  Tolerance: BASELINE.json north_star."""
+    import numpy as np
+    import torch
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'full_bench_b8.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    ly, lx = meta['lattice']
+    g = torch.from_numpy(z['mask'])
+    m = mask[meta['samples']].cpu()[:, :, :, ::ly, ::lx]
+    f = flags[meta['samples']].cpu()
+    res = {'source': 'tests/golden/full_bench_b8.npz (unmodified reference, fp32 CPU)', 'clips': meta['samples'],
+           'max_dlogit': (m - g).abs().max().item(), 'min_iou': min(mask_iou(m[i], g[i]) for i in range(g.shape[0])),
+           'flags_max_err': (f - torch.from_numpy(z['flags'])).abs().max().item(), 'tol_dlogit': 1e-2, 'tol_iou': 0.99}
+    res['ok'] = bool(res['max_dlogit'] <= 1e-2 and res['min_iou'] >= 0.99 and res['flags_max_err'] <= 2e-2)
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -137,13 +316,7 @@ def run_ours(args):
     import tcow_b200
     from tcow_b200 import synth
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    world, rank, local, dev = dist_env()
     peaks = load_peaks()
 
     net = tcow_b200.Seeker(logging.getLogger('bench'), **SEEKER_KW)
@@ -154,33 +327,15 @@ def run_ours(args):
         eng.max_chunk = args.chunk
     B = args.batch
     # 3 queries per video (README.md:42): clips come in triples sharing the RGB and differing in the query.
-    rgb_l, q_l = [], []
-    for i in range(B):
-        vid = (rank * B + i) // 3
-        r, _ = synth.make_clip(vid, T, HF, WF)
-        _, q = synth.make_clip(1000 + rank * B + i, T, HF, WF)
-        rgb_l.append(r); q_l.append(q)
-    rgb_h = torch.stack(rgb_l).pin_memory()
-    q_h = torch.stack(q_l).pin_memory()
+    rgb_f, q_f = synth.bench_clips(rank, B, T, HF, WF)
+    rgb_h, q_h = rgb_f.pin_memory(), q_f.pin_memory()
     rgb_d, q_d = rgb_h.to(dev), q_h.to(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     with torch.no_grad():
         # ---------------------------------------------------------- device-resident throughput (`value`)
         for _ in range(args.warmup):
             net(rgb_d, q_d)
-        barrier()
+        barrier(world)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -189,54 +344,40 @@ def run_ours(args):
         e0.record()
         launches = 0
         for _ in range(args.steps):
-            net(rgb_d, q_d)
+            mask, flags = net(rgb_d, q_d)
             launches += eng.launches
         e1.record()
-        barrier()
-        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        barrier(world)
+        ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
         clocks = sampler.stop() if rank == 0 else None
         prof, eng.profile = eng.profile, None
+        # the batch that was just timed, checked against the reference's own outputs (rank 0 holds the fixture's clips)
+        parity = golden_parity(mask, flags) if (rank == 0 and B == 8) else None
+        ours_mask = mask if rank == 0 else None
+        del mask, flags
 
-        # ---------------------------------------------------------- end to end through Seeker.forward with host buffers
-        res_h = torch.empty((B, T, 3), dtype=torch.float32).pin_memory()
-        area_h = torch.empty((B, 3, T), dtype=torch.float32).pin_memory()
-        # Inputs start in pinned host memory every step; a copy stream uploads step i+1 while step i computes
-        # (what a DataLoader with pin_memory + non_blocking does); the step's result is read back to the host.
-        copy_stream = torch.cuda.Stream(device=dev)
-        cur = torch.cuda.current_stream()
-        bufs = [(torch.empty_like(rgb_d), torch.empty_like(q_d)) for _ in range(2)]
-        ev_ready = [torch.cuda.Event() for _ in range(2)]
-        ev_free = [torch.cuda.Event() for _ in range(2)]
+    # -------------------------------------------------------------- end to end through Seeker.forward with host buffers
+    # (1) decoder-style inputs: uint8 frames + uint8 query masks in pinned host memory (what a video decoder / the loader
+    #     hold before data/data_plugin.py:174 expands them), scaled by 1/255 in the gather kernel;
+    # (2) the reference loader's fp32 tensors (data_plugin.py:199-200), 4x the upload.  Both read back the full logits.
+    rgb_u8 = (rgb_f * 255.0).round().to(torch.uint8).pin_memory()
+    q_u8 = q_f.to(torch.uint8).pin_memory()
+    e2e_ms, e2e_h2d, e2e_d2h, out_last = e2e_measure(net, rgb_u8, q_u8, 1.0 / 255.0, args.steps, args.warmup, world, dev)
+    e2e_par = None
+    if rank == 0:
+        # the uint8 path against the fp32 path on the same (quantised) frames: differs only by the rounding of x*(1/255) vs x/255 before the bf16 cast
+        with torch.no_grad():
+            m_ref, _ = net((rgb_u8.float() / 255.0).to(dev), q_d)
+        e2e_par = {'max_dlogit_u8_vs_f32_inputs': (out_last[0].to(dev) - m_ref).abs().max().item()}
+        del m_ref
+    f32_ms, f32_h2d, f32_d2h, _ = e2e_measure(net, rgb_h, q_h, 1.0, args.steps, args.warmup, world, dev)
 
-        def upload(i):
-            k = i & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_free[k])
-                bufs[k][0].copy_(rgb_h, non_blocking=True)
-                bufs[k][1].copy_(q_h, non_blocking=True)
-                ev_ready[k].record(copy_stream)
-
-        def e2e_run(n):
-            for k in range(2):
-                ev_free[k].record(cur)
-            upload(0)
-            for i in range(n):
-                if i + 1 < n:
-                    upload(i + 1)
-                k = i & 1
-                cur.wait_event(ev_ready[k])
-                mask, flags = net(bufs[k][0], bufs[k][1])
-                ev_free[k].record(cur)
-                res_h.copy_(flags, non_blocking=True)
-                area_h.copy_((mask > 0).float().mean(dim=(3, 4)), non_blocking=True)   # per-frame mask area read back
-                cur.synchronize()
-
-        e2e_run(min(args.warmup, 3))
-        barrier()
-        t0 = time.perf_counter()
-        e2e_run(args.steps)
-        barrier()
-        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    # -------------------------------------------------------------- training step under the same clock (BASELINE configs[3])
+    train = None
+    if not args.no_train:
+        eng.release()
+        torch.cuda.empty_cache()
+        train = train_measure(args, world, rank, local, dev, steps=args.train_steps, warmup=3, clocks=False)
 
     if rank != 0:
         if world > 1:
@@ -259,6 +400,8 @@ def run_ours(args):
                      'gbs': round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[2] and v[0] else None}
                  for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
     step_tflops = value / world * FLOP_PER_CLIP / 1e12
+    traffic = load_traffic()
+    gemm_traffic = (traffic or {}).get('classes', {}).get('gemm_bf16_tn_kernel') if B == 8 else None
 
     line = {
         'metric': 'seeker_fwd_clips_per_s', 'value': value, 'unit': 'clips/s', 'n_gpus': world, 'steps': args.steps,
@@ -269,26 +412,37 @@ def run_ours(args):
                                f'and residual stream (BASELINE configs[1])',
                    'batch_per_gpu': B, 'parallelism': f'replicas x{world}, no collective',
                    'l2': 'activation working set ~1.2 GB per step >> 126 MB L2; no flush needed'},
-        'roofline': {'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
-                     'frac': round(achieved / peaks['sustained'], 4),
-                     # dram__bytes_read+write per launch, launch-weighted mean over the step's GEMM classes, from the
-                     # `ncu --set full` capture summarised in profiles/r01e_ncu_full.txt (B=8; bytes: qkv 392e6 x24,
-                     # fc1 502e6 x12, fc2 860e6 x12, proj 497e6 x24); algorithmic mean 583e6 — no operand re-reads
-                     'traffic': 523.3e6 if B == 8 else None, 'traffic_unit': 'bytes/launch',
-                     'traffic_source': 'profiles/r01e_ncu_full.txt',
-                     'kernel': 'gemm_bf16_tn_kernel (tcgen05), all launches of the step',
-                     'launches_per_step': gemm_n // args.steps, 'gemm_ms_per_step': round(gemm_ms / args.steps, 3),
-                     'peak_source': peaks['source'] + ' bf16_tflops_sustained (kernel timed inside a long step)',
+        'roofline': {'bound': 'tensor',
+                     # whole step first: algorithmic FLOPs of the reference forward over the step time
                      'step_tflops_algorithmic': round(step_tflops, 1),
                      'step_frac_of_burst_peak': round(step_tflops / peaks['burst'], 4),
-                     'step_frac_of_sustained_peak': round(step_tflops / peaks['sustained'], 4)},
+                     'step_frac_of_sustained_peak': round(step_tflops / peaks['sustained'], 4),
+                     # dominant kernel: 2MNK of every GEMM launch of the step over their CUDA-event durations
+                     'achieved': round(achieved, 1), 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
+                     'frac': round(achieved / peaks['sustained'], 4),
+                     'frac_of_burst_peak': round(achieved / peaks['burst'], 4),
+                     'traffic': None if gemm_traffic is None else gemm_traffic['dram_bytes_per_launch'],
+                     'traffic_unit': 'bytes/launch',
+                     'traffic_source': None if traffic is None else traffic.get('source'),
+                     'kernel': 'gemm_bf16_tn_kernel (tcgen05), all launches of the step',
+                     'launches_per_step': gemm_n // args.steps, 'gemm_ms_per_step': round(gemm_ms / args.steps, 3),
+                     'peak_source': peaks['source'] + ' bf16_tflops_sustained (kernel timed inside a long step)'},
+        'parity': parity,
         'breakdown': breakdown,
         'clocks': clocks,
-        'e2e': {'value': world * B * args.steps / (e2e_ms * 1e-3), 'unit': 'clips/s',
-                'h2d_bytes_per_step': int(rgb_h.numel() * 4 + q_h.numel() * 4),
-                'd2h_bytes_per_step': int(res_h.numel() * 4 + area_h.numel() * 4), 'ms_per_step': e2e_ms / args.steps},
+        'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': e2e_h2d,
+                'd2h_bytes_per_step': e2e_d2h, 'ms_per_step': e2e_ms,
+                'inputs': 'uint8 frames + uint8 query masks in pinned host memory (decoder format), x1/255 in the gather kernel',
+                'outputs': 'full (B,3,T,Hf,Wf) fp32 logits + flags copied to pinned host memory every step', **(e2e_par or {})},
+        'e2e_f32_inputs': {'value': world * B / (f32_ms * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': f32_h2d,
+                           'd2h_bytes_per_step': f32_d2h, 'ms_per_step': f32_ms,
+                           'inputs': "fp32 frames + fp32 query masks, the reference loader's tensors (data_plugin.py:199-200)"},
         'gpu_launches': launches,
     }
+    if train is not None:
+        line['train'] = train
+    if world == 1 and not args.no_eager_baseline:
+        line['gpu_eager_baseline'] = eager_gpu_baseline(dev, rgb_d, q_d, ours_mask, args.steps, args.warmup)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         times = cpu_forward_timing(3, cores)[1:]
@@ -298,24 +452,43 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity['ok']:
+        raise SystemExit(f'bench: the timed batch disagrees with the reference golden vectors: {parity}')
 
 
-def run_train(args):
-    """--workload train (BASELINE configs[3]): fwd + bwd + AdamW step, 2 videos x 3 queries per GPU, data-parallel with
-    the bucketed gradient all-reduce of tcow_b200/ddp.py overlapped with the backward (NCCL over NVLink)."""
+def run_eager(args):
+    """--impl eager: the reference algorithm under stock eager PyTorch on the GPU (autocast bf16), same line format."""
+    import torch
+
+    from tcow_b200 import synth
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    B = args.batch
+    rgb, q = synth.bench_clips(0, B, T, HF, WF)
+    rgb, q = rgb.to(dev), q.to(dev)
+    r = eager_gpu_baseline(dev, rgb, q, torch.zeros((B, 3, T, HF, WF), device=dev), args.steps, args.warmup)
+    v = r['autocast_bf16']['clips_per_s']
+    line = {'impl': 'eager', 'metric': 'seeker_fwd_clips_per_s', 'value': v, 'unit': 'clips/s', 'n_gpus': 1,
+            'steps': max(3, args.steps // 2), 'warmup': max(2, args.warmup // 2), 'ms_per_step': r['autocast_bf16']['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': f'TCOW Seeker forward, T=30 240x320, causal, batch {B}: the reference algorithm under stock '
+                                   f'eager PyTorch torch.autocast(cuda, bf16) on one B200 (cuBLAS/cuDNN/ATen kernels)'},
+            'gpu_eager_baseline': {k: v for k, v in r.items() if k != 'ours_vs_fp32_eager'}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def train_measure(args, world, rank, local, dev, steps, warmup, clocks=True):
+    """BASELINE configs[3]: fwd + hand-written bwd + fused AdamW, 2 videos x 3 queries per GPU, data-parallel with the
+    bucketed gradient all-reduce of tcow_b200/ddp.py overlapped with the backward (NCCL over NVLink; train.py:86-102,
+    222-223).  Returns the JSON record on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
 
     import tcow_b200
     from tcow_b200 import ddp, synth
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
     peaks = load_peaks()
     kw = dict(SEEKER_KW)
     kw['drop_path_rate'] = args.drop_path
@@ -337,11 +510,6 @@ def run_train(args):
     tm, tf = synth.make_targets(list(range(rank * B, rank * B + B)), T, HF, WF)
     tm, tf = tm.to(dev), tf.to(dev)
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, fused=True)       # args.py:108,179 defaults
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # Inputs start in pinned host memory every step; a copy stream uploads step i+1 while step i computes (what a
     # DataLoader with pin_memory + non_blocking does, train.py's loaders included).
@@ -379,35 +547,32 @@ def run_train(args):
         opt.step()
         return loss
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    barrier(world)
+    sampler = ClockSampler(local) if (clocks and rank == 0) else None
+    if sampler is not None:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     exposed = []
     launches = 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
         launches += eng.launches
         if sync is not None:
             exposed.append(sync.exposed_time_ms())
     e1.record()
     loss_val = float(loss.detach())       # the step's result read back to the host
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    clk = sampler.stop() if sampler is not None else None
     # per-kernel-class breakdown of one more (untimed) step
     eng.profile = []
     step()
     torch.cuda.synchronize()
     prof, eng.profile = eng.profile, None
+    line = None
     if rank == 0:
         agg = {}
         for kind, flops, nbytes, a, b in prof:
@@ -419,10 +584,10 @@ def run_train(args):
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
         gemm = [v for k, v in agg.items() if k.startswith(('gemm', 'dgrad', 'wgrad'))]
         gemm_ms, gemm_fl = sum(v[0] for v in gemm), sum(v[1] for v in gemm)
-        ms_step = ms / args.steps
-        value = world * B * args.steps / (ms * 1e-3)
+        ms_step = ms / steps
+        value = world * B * steps / (ms * 1e-3)
         line = {'metric': 'seeker_train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
-                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+                'steps': steps, 'warmup': warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
                 'config': {'workload': f'TCOW Seeker training step (fwd + hand-written bwd + fused AdamW), T=30 240x320, causal, '
                                        f'{V} videos x {Q} queries per GPU, drop_path_rate={args.drop_path}, data-parallel x{world} '
@@ -437,10 +602,21 @@ def run_train(args):
                              'step_frac_of_burst_peak': round(3 * FLOP_PER_CLIP * B / (ms_step * 1e-3) / 1e12 / peaks['burst'], 4)},
                 'allreduce': {'bytes_per_step': int(eng.last_flat.numel() * 4) if eng.last_flat is not None else None,
                               'exposed_ms_per_step': round(statistics.mean(x for x in exposed if x is not None), 3) if exposed and exposed[0] is not None else 0.0},
-                'breakdown': breakdown, 'clocks': clocks, 'loss': loss_val,
+                'breakdown': breakdown, 'clocks': clk, 'loss': loss_val,
                 'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': int(rgb_h.numel() * 4 + q_h.numel() * 4),
                         'd2h_bytes_per_step': 4, 'note': 'inputs are uploaded from pinned host memory every step on a copy stream (double-buffered)'},
                 'gpu_launches': launches}
+    del net, opt, eng, bufs
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_train(args):
+    """--workload train: the training record alone (it is also the `train` sub-record of the default line)."""
+    import torch.distributed as dist
+    world, rank, local, dev = dist_env()
+    line = train_measure(args, world, rank, local, dev, steps=args.steps, warmup=args.warmup)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -526,34 +702,22 @@ def run_hires(args):
     import tcow_b200
     from tcow_b200 import synth
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    world, rank, local, dev = dist_env()
     peaks = load_peaks()
     Th, Hh, Wh = 60, 480, 640
     kw = dict(SEEKER_KW, num_total_frames=Th, num_visible_frames=Th, frame_height=Hh, frame_width=Wh, causal_attention=0)
     net = tcow_b200.Seeker(logging.getLogger('bench'), **kw)
     net.load_state_dict(synth.make_state_dict(901, num_frames=Th, frame_height=Hh, frame_width=Wh))
     net = net.to(dev).eval()
-    rgb_h, q_h = synth.make_batch([rank], num_frames=Th, frame_height=Hh, frame_width=Wh)
-    rgb_h, q_h = rgb_h.pin_memory(), q_h.pin_memory()
+    rgb_f, q_f = synth.make_batch([20 + rank], num_frames=Th, frame_height=Hh, frame_width=Wh)
     flop = 20878.31e9          # equals FlopCounterMode on the reference
     eng = net.seeker.engine()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     with torch.no_grad():
-        rgb, q = rgb_h.to(dev), q_h.to(dev)
+        rgb, q = rgb_f.to(dev), q_f.to(dev)
         for _ in range(args.warmup):
             net(rgb, q)
-        barrier()
+        barrier(world)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -561,51 +725,29 @@ def run_hires(args):
         e0.record()
         launches = 0
         for _ in range(args.steps):
-            net(rgb, q)
+            mask, flags = net(rgb, q)
             launches += eng.launches
         e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+        barrier(world)
+        ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
         clocks = sampler.stop() if rank == 0 else None
-        # end to end: the clip starts in pinned host memory every step (copy stream, double-buffered: clip i+1 uploads
-        # while clip i computes); flags + per-frame mask areas are read back every step
-        copy_stream = torch.cuda.Stream(device=dev)
-        cur = torch.cuda.current_stream()
-        bufs = [(torch.empty_like(rgb), torch.empty_like(q)) for _ in range(2)]
-        ev_ready = [torch.cuda.Event() for _ in range(2)]
-        ev_free = [torch.cuda.Event() for _ in range(2)]
-        res_f = torch.empty((1, Th, 3), dtype=torch.float32).pin_memory()
-        res_a = torch.empty((1, 3, Th), dtype=torch.float32).pin_memory()
-
-        def upload(i):
-            k = i & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_free[k])
-                bufs[k][0].copy_(rgb_h, non_blocking=True)
-                bufs[k][1].copy_(q_h, non_blocking=True)
-                ev_ready[k].record(copy_stream)
-
-        for k in range(2):
-            ev_free[k].record(cur)
-        upload(0)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            if i + 1 < args.steps:
-                upload(i + 1)
-            k = i & 1
-            cur.wait_event(ev_ready[k])
-            mask, flags = net(bufs[k][0], bufs[k][1])
-            ev_free[k].record(cur)
-            res_f.copy_(flags, non_blocking=True)
-            res_a.copy_((mask > 0).float().mean(dim=(3, 4)), non_blocking=True)
-            cur.synchronize()
-        barrier()
-        e2e_ms = 1e3 * (time.perf_counter() - t0)
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        parity = None
+        if rank == 0:
+            # the clip that was just timed is the one the unmodified reference ran for tests/golden/hires_causal0.npz
+            import numpy as np
+            z = np.load(os.path.join(ROOT, 'tests', 'golden', 'hires_causal0.npz'))
+            meta = json.loads(bytes(z['meta']).decode())
+            ly, lx = meta['lattice']
+            g = torch.from_numpy(z['mask'])
+            m = mask.cpu()[:, :, :, ::ly, ::lx]
+            parity = {'source': 'tests/golden/hires_causal0.npz (unmodified reference, fp32 CPU)',
+                      'max_dlogit': (m - g).abs().max().item(), 'min_iou': mask_iou(m, g),
+                      'flags_max_err': (flags.cpu() - torch.from_numpy(z['flags'])).abs().max().item()}
+        del mask, flags
+    # end to end: uint8 clip in pinned host memory every step, full logits read back (see e2e_measure)
+    rgb_u8 = (rgb_f * 255.0).round().to(torch.uint8).pin_memory()
+    q_u8 = q_f.to(torch.uint8).pin_memory()
+    e2e_ms, h2d, d2h, _ = e2e_measure(net, rgb_u8, q_u8, 1.0 / 255.0, args.steps, args.warmup, world, dev)
     if rank == 0:
         value = world * args.steps / (ms * 1e-3)
         tfl = value / world * flop / 1e12
@@ -619,10 +761,9 @@ def run_hires(args):
             'roofline': {'bound': 'tensor', 'achieved': round(tfl, 1), 'peak': peaks['burst'], 'unit': 'TFLOP/s',
                          'frac': round(tfl / peaks['burst'], 4), 'traffic': None,
                          'kernel': 'whole step, algorithmic FLOPs of the reference forward (20 878 GFLOP per clip)'},
-            'clocks': clocks,
-            'e2e': {'value': world * args.steps / (e2e_ms * 1e-3), 'unit': 'clips/s',
-                    'h2d_bytes_per_step': int(rgb_h.numel() * 4 + q_h.numel() * 4),
-                    'd2h_bytes_per_step': int((3 * Th + Th * 3) * 4)},
+            'parity': parity, 'clocks': clocks,
+            'e2e': {'value': world / (e2e_ms * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': e2e_ms},
             'gpu_launches': launches}), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -634,8 +775,11 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=BATCH)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'eager'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-eager-baseline', action='store_true', help='skip the stock-PyTorch-on-GPU baseline leg')
+    ap.add_argument('--no-train', action='store_true', help='skip the training sub-record (BASELINE configs[3]) of the default line')
+    ap.add_argument('--train-steps', type=int, default=10, help='timed training steps of the `train` sub-record')
     ap.add_argument('--chunk', type=int, default=0, help='clips per engine pass (0 = engine default)')
     ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'sweep', 'hires'],
                     help='infer = BASELINE configs[1] (the headline metric, default); train = configs[3] (fwd+bwd+AdamW, DDP); '
@@ -650,6 +794,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     if args.impl == 'reference':
         run_reference(args)
+    elif args.impl == 'eager':
+        run_eager(args)
     elif args.workload == 'train':
         run_train(args)
     elif args.workload == 'sweep':

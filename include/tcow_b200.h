@@ -108,6 +108,16 @@ int tcow_cls_merge(const float* out_cls, void* out, int64_t ld_out, int B, int T
 int tcow_patch_gather(const float* frames, const float* query, void* P, int B, int T, int Hf, int Wf,
                       int patch, int normalize, int queries_per_video, int sample0, void* stream);
 
+/* The same gather reading the frames and/or the query mask as uint8 (TCOW_DTYPE_U8) — the form a video decoder and the
+ * reference's loader hold them in before data/data_plugin.py:174 (`rgb / 255.0`) and :182-185 (uint8 query mask) expand
+ * them on the host.  RGB values are multiplied by frame_scale (1/255 reproduces :174; 1.0 is the plain cast of
+ * mask_tracker.py:103) before the optional normalisation; a clip then crosses PCIe as 9.2 MB instead of 36.9 MB. */
+#define TCOW_DTYPE_F32 0
+#define TCOW_DTYPE_U8 1
+int tcow_patch_gather_typed(const void* frames, int frames_dtype, const void* query, int query_dtype, void* P, int B,
+                            int T, int Hf, int Wf, int patch, int normalize, float frame_scale, int queries_per_video,
+                            int sample0, void* stream);
+
 /* Residual-stream initialisation (vision_tf.py:99-138): X[(b*N+n)*T+t,:] = conv_bias + pos_embed[1+n] +
  * time_embed[t];  X[M+b,:] = cls_token + pos_embed[0].  The patch GEMM then accumulates into X. */
 int tcow_embed_init(float* X, const float* conv_bias, const float* pos_embed, const float* time_embed,

@@ -38,6 +38,10 @@ CASES = [
     dict(name='full_causal1', T=30, Hf=240, Wf=320, samples=[0, 1], causal=1, lattice=(7, 9)),
     # more than 304 tokens per frame and more than 32 frames: the long-sequence kernels (config 5 in miniature)
     dict(name='long_causal0', T=34, Hf=256, Wf=320, samples=[12], causal=0, lattice=(5, 7)),
+    # BASELINE configs[4] at its real shape: S=1201 tokens per frame, cls mean over 60 frames (vit.py:195); ~2 min on CPU
+    dict(name='hires_causal0', T=60, Hf=480, Wf=640, samples=[20], causal=0, lattice=(9, 11)),
+    # clips 0 and 7 of the batch bench.py times on rank 0 (synth.bench_clips): the bench asserts them after the timed loop
+    dict(name='full_bench_b8', T=30, Hf=240, Wf=320, samples=[0, 7], bench_batch=8, causal=1, lattice=(7, 9)),
 ]
 WEIGHT_SEED = 901
 
@@ -56,8 +60,12 @@ def run_case(c):
     net = ref_import.build_reference(sd, **kwargs)
     if c.get('pretrained_norm'):
         net.seeker.tracker_backbone.pretrained = True      # SURVEY §8(c) trap 5
-    rgb, q = synth.make_batch(c['samples'], num_frames=T, frame_height=Hf, frame_width=Wf,
-                              query_frame=c.get('query_frame', 0))
+    if 'bench_batch' in c:
+        rgb, q = synth.bench_clips(0, c['bench_batch'], T, Hf, Wf)
+        rgb, q = rgb[c['samples']], q[c['samples']]
+    else:
+        rgb, q = synth.make_batch(c['samples'], num_frames=T, frame_height=Hf, frame_width=Wf,
+                                  query_frame=c.get('query_frame', 0))
     t0 = time.time()
     with torch.no_grad():
         mask, flags = net(rgb.clone(), q.clone())

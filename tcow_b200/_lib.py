@@ -32,6 +32,8 @@ SIGNATURES = {
     'tcow_cls_merge': [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_int, c_void_p],
     'tcow_patch_gather': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_void_p],
+    'tcow_patch_gather_typed': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                c_int, c_int, c_void_p],
     'tcow_embed_init': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'tcow_mask_upsample': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                            c_void_p],

@@ -9,11 +9,28 @@
 
 namespace tcow {
 
-// One thread per 8 consecutive K elements (16 bytes of bf16 out, 32 bytes of fp32 in).
+// One thread per 8 consecutive K elements (16 bytes of bf16 out; 32 bytes of fp32 or 8 bytes of uint8 in).
 // K index = c*P*P + r*P + w (Conv2d weight layout (D, C, P, P) flattened), P % 8 == 0.
-__global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ frames, const float* __restrict__ query,
+// FT / QT: element type of the frames / the query mask — float, or uint8_t as a video decoder and the data loader leave
+// them (data/data_plugin.py:174 divides the integer frames by 255 on the host; `frame_scale` does it here instead).
+__device__ __forceinline__ void load8(const float* src, float (&v)[8]) {
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+  const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const uint8_t* src, float (&v)[8]) {
+  const uint2 a = __ldcs(reinterpret_cast<const uint2*>(src));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = static_cast<float>((a.x >> (8 * i)) & 0xffu);
+    v[4 + i] = static_cast<float>((a.y >> (8 * i)) & 0xffu);
+  }
+}
+
+template <typename FT, typename QT>
+__global__ void __launch_bounds__(256) patch_gather_kernel(const FT* __restrict__ frames, const QT* __restrict__ query,
                                                            __nv_bfloat16* __restrict__ Pm, int B, int T, int Hf, int Wf,
-                                                           int P, int normalize, int qpv, int sample0) {
+                                                           int P, int normalize, float frame_scale, int qpv, int sample0) {
   const int Ho = Hf / P, Wo = Wf / P, N = Ho * Wo;
   const int K = 4 * P * P, KC = K / 8;
   const long long total = static_cast<long long>(B) * N * T * KC;
@@ -28,17 +45,23 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
     const int c = k / (P * P), r = (k / P) % P, w = k % P;
     const int y = (n / Wo) * P + r, x = (n % Wo) * P + w;
     const int vid = (sample0 + b) / qpv;  // queries of one video share its RGB frames (pipeline.py:134-158)
-    const float* src = (c < 3) ? frames + (((static_cast<long long>(vid) * 3 + c) * T + t) * Hf + y) * Wf + x
-                               : query + ((static_cast<long long>(b) * T + t) * Hf + y) * Wf + x;
-    float4 v0 = __ldcs(reinterpret_cast<const float4*>(src));
-    float4 v1 = __ldcs(reinterpret_cast<const float4*>(src) + 1);
-    if (normalize && c < 3) {
-      const float m = 0.45f, s = 0.225f;  // vision_tf.py:23-24
-      v0.x = (v0.x - m) / s; v0.y = (v0.y - m) / s; v0.z = (v0.z - m) / s; v0.w = (v0.w - m) / s;
-      v1.x = (v1.x - m) / s; v1.y = (v1.y - m) / s; v1.z = (v1.z - m) / s; v1.w = (v1.w - m) / s;
+    float v[8];
+    if (c < 3) {
+      load8(frames + (((static_cast<long long>(vid) * 3 + c) * T + t) * Hf + y) * Wf + x, v);
+      if (frame_scale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= frame_scale;
+      }
+      if (normalize) {
+        const float m = 0.45f, s = 0.225f;  // vision_tf.py:23-24
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - m) / s;
+      }
+    } else {
+      load8(query + ((static_cast<long long>(b) * T + t) * Hf + y) * Wf + x, v);
     }
-    uint4 o = make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
-    reinterpret_cast<uint4*>(Pm)[i] = o;
+    reinterpret_cast<uint4*>(Pm)[i] =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
 }
 
@@ -78,19 +101,39 @@ static int grid_for(long long total, int threads) {
 
 }  // namespace tcow
 
-extern "C" int tcow_patch_gather(const float* frames, const float* query, void* P, int B, int T, int Hf, int Wf,
-                                 int patch, int normalize, int queries_per_video, int sample0, void* stream) {
+extern "C" int tcow_patch_gather_typed(const void* frames, int frames_dtype, const void* query, int query_dtype, void* P,
+                                       int B, int T, int Hf, int Wf, int patch, int normalize, float frame_scale,
+                                       int queries_per_video, int sample0, void* stream) {
   using namespace tcow;
   if (!frames || !query || !P || B <= 0 || T <= 0 || queries_per_video < 1 || sample0 < 0)
     return set_error(TCOW_ERR_ARG, "patch_gather: bad argument");
+  if ((frames_dtype != TCOW_DTYPE_F32 && frames_dtype != TCOW_DTYPE_U8) ||
+      (query_dtype != TCOW_DTYPE_F32 && query_dtype != TCOW_DTYPE_U8))
+    return set_error(TCOW_ERR_ARG, "patch_gather: dtype must be TCOW_DTYPE_F32 or TCOW_DTYPE_U8");
   if (patch % 8 != 0 || Hf % patch != 0 || Wf % patch != 0)
     return set_error(TCOW_ERR_ARG, "patch_gather: frame %dx%d not divisible by patch %d (or patch %% 8 != 0)", Hf, Wf, patch);
-  if ((reinterpret_cast<uintptr_t>(frames) & 15) || (reinterpret_cast<uintptr_t>(query) & 15) || (Wf % 4))
-    return set_error(TCOW_ERR_ARG, "patch_gather: inputs must be 16-byte aligned, contiguous, width %% 4 == 0");
+  const uintptr_t fa = frames_dtype == TCOW_DTYPE_F32 ? 15 : 7, qa = query_dtype == TCOW_DTYPE_F32 ? 15 : 7;
+  if ((reinterpret_cast<uintptr_t>(frames) & fa) || (reinterpret_cast<uintptr_t>(query) & qa) || (Wf % 8))
+    return set_error(TCOW_ERR_ARG, "patch_gather: inputs must be 16-byte (fp32) / 8-byte (uint8) aligned, contiguous, width %% 8 == 0");
   const long long total = static_cast<long long>(B) * (Hf / patch) * (Wf / patch) * T * (4 * patch * patch / 8);
-  patch_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      frames, query, static_cast<__nv_bfloat16*>(P), B, T, Hf, Wf, patch, normalize, queries_per_video, sample0);
+  const int grid = grid_for(total, 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(P);
+#define TCOW_PG(FT, QT)                                                                                              \
+  patch_gather_kernel<FT, QT><<<grid, 256, 0, st>>>(static_cast<const FT*>(frames), static_cast<const QT*>(query), out, B, \
+                                                    T, Hf, Wf, patch, normalize, frame_scale, queries_per_video, sample0)
+  if (frames_dtype == TCOW_DTYPE_F32 && query_dtype == TCOW_DTYPE_F32) TCOW_PG(float, float);
+  else if (frames_dtype == TCOW_DTYPE_F32) TCOW_PG(float, uint8_t);
+  else if (query_dtype == TCOW_DTYPE_F32) TCOW_PG(uint8_t, float);
+  else TCOW_PG(uint8_t, uint8_t);
+#undef TCOW_PG
   return check_launch("patch_gather_kernel");
+}
+
+extern "C" int tcow_patch_gather(const float* frames, const float* query, void* P, int B, int T, int Hf, int Wf,
+                                 int patch, int normalize, int queries_per_video, int sample0, void* stream) {
+  return tcow_patch_gather_typed(frames, TCOW_DTYPE_F32, query, TCOW_DTYPE_F32, P, B, T, Hf, Wf, patch, normalize, 1.0f,
+                                 queries_per_video, sample0, stream);
 }
 
 extern "C" int tcow_embed_init(float* X, const float* conv_bias, const float* pos_embed, const float* time_embed,

@@ -132,7 +132,13 @@ def attach(seeker_module, process_group=None, average=True, bucket_bytes=25 << 2
 def broadcast_parameters(module, src=0, process_group=None):
     if not (dist.is_available() and dist.is_initialized()):
         return
-    for p in module.parameters():
-        dist.broadcast(p.data, src=src, group=process_group)
-    for b in module.buffers():
-        dist.broadcast(b.data, src=src, group=process_group)
+    # p.detach() shares the parameter's version counter (p.data does not): the in-place write of the broadcast bumps
+    # p._version, which is what SeekerEngine's packed-weight / CUDA-graph cache is stamped with (engine.py:_stamp)
+    with torch.no_grad():
+        for p in module.parameters():
+            dist.broadcast(p.detach(), src=src, group=process_group)
+        for b in module.buffers():
+            dist.broadcast(b.detach(), src=src, group=process_group)
+    tracker = getattr(module, 'seeker', module)
+    if getattr(tracker, '_engine', None) is not None:
+        tracker._engine.invalidate()

@@ -61,13 +61,18 @@ class SeekerEngine:
         self.use_cuda_graph = os.environ.get('TCOW_CUDA_GRAPH', '1') != '0'
         self._graphs = {}      # key -> (torch.cuda.CUDAGraph, launches) ; key -> int warm-up count in _warm
         self._warm = {}
+        self.max_cached_shapes = 4   # graphs / workspaces kept per device (LRU); nn.DataParallel threads share the engine
 
     # ------------------------------------------------------------------ weights
     @staticmethod
     def _stamp(mod):
-        # walk the modules' own tensors rather than parameters(): nn.DataParallel replicas (train.py:223) hold plain
-        # tensors in _parameters and report no parameters(), and a stale stamp would mean stale packed weights
-        return tuple((p.data_ptr(), p._version) for m in mod.modules() for p in m._parameters.values() if p is not None)
+        # walk the modules' own tensors rather than parameters(): nn.DataParallel replicas (train.py:223) report no
+        # parameters() — replicate() leaves them an empty _parameters and the broadcast copies in _former_parameters —
+        # and a stale stamp would mean stale packed weights
+        def tensors(m):
+            yield from m._parameters.values()
+            yield from getattr(m, '_former_parameters', {}).values()
+        return tuple((p.data_ptr(), p._version) for m in mod.modules() for p in tensors(m) if p is not None)
 
     def _pack(self, mod, device):
         bb = mod.tracker_backbone.timesformer.model
@@ -148,10 +153,26 @@ class SeekerEngine:
             self._graphs = {k: v for k, v in self._graphs.items() if k[0] != device.index}   # they hold the old weights
         return pk
 
+    def invalidate(self):
+        """Forget the packed weights and the captured graphs.  The cache key is (data_ptr, _version) of every parameter,
+        which in-place writes through `.data` (p.data.copy_(), an EMA swap) do not change — call this after such a write."""
+        with self._lock:
+            self._packed.clear()
+            self._graphs.clear()
+            self._warm.clear()
+
+    def release(self):
+        """invalidate() and drop the activation workspaces as well (returns the memory to the caching allocator)."""
+        self.invalidate()
+        with self._lock:
+            self._workspace.clear()
+
     def _ws(self, device, Bc, N, T, D, K_patch, n_pad):
         key = (device.index, Bc, N, T, D, K_patch, n_pad)
         with self._lock:
-            ws = self._workspace.get(key)
+            ws = self._workspace.pop(key, None)
+            if ws is not None:
+                self._workspace[key] = ws                      # most recently used last
         if ws is None:
             M = Bc * N * T
             R = M + Bc
@@ -161,7 +182,15 @@ class SeekerEngine:
                       OCLS=e((Bc, T, D), torch.float32), LOW=e((M, n_pad), torch.float32))
             with self._lock:
                 self._workspace[key] = ws
+                self._evict(self._workspace, device.index, self.max_cached_shapes)
         return ws
+
+    @staticmethod
+    def _evict(cache, device_index, limit):
+        """Least-recently-used eviction per device (dict order = use order); caller holds the lock."""
+        mine = [k for k in cache if k[0] == device_index]
+        for k in mine[:max(0, len(mine) - limit)]:
+            del cache[k]
 
     def _launch(self, kind, fn, *args, flops=0.0, nbytes=0.0):
         if self.profile is None:
@@ -181,9 +210,12 @@ class SeekerEngine:
                      nbytes=2.0 * (M * K + N * K) + out.element_size() * M * N * (2 if epi == EPI_F32_ADD else 1))
 
     # ------------------------------------------------------------------ forward
-    def forward(self, mod, input_frames, query_mask, queries_per_video=1):
+    def forward(self, mod, input_frames, query_mask, queries_per_video=1, frame_scale=1.0):
         """input_frames (V,3,T,Hf,Wf); query_mask (V*queries_per_video,1,T,Hf,Wf), sample s belongs to video
-        s // queries_per_video.  queries_per_video=1 is the reference's Seeker.forward contract."""
+        s // queries_per_video.  queries_per_video=1 is the reference's Seeker.forward contract.
+        fp32 and uint8 inputs are read as they are (no staging copy); other dtypes are cast to fp32 first, as
+        mask_tracker.py:103-104 does.  frame_scale multiplies the RGB values in the gather kernel: 1/255 turns decoder-style
+        uint8 frames into the [0,1] floats data/data_plugin.py:174 builds on the host."""
         if not input_frames.is_cuda:
             raise RuntimeError('tcow_b200 runs on a CUDA sm_100 device only; move the module and inputs to '
                                'the GPU (there is no CPU fallback)')
@@ -218,8 +250,9 @@ class SeekerEngine:
         with torch.cuda.device(device):
             _lib.call('tcow_check_device')
             pk = self.packed(mod, device)
-            frames = input_frames.to(torch.float32).contiguous()
-            query = query_mask.to(torch.float32).contiguous()
+            as_is = (torch.float32, torch.uint8)
+            frames = (input_frames if input_frames.dtype in as_is else input_frames.to(torch.float32)).contiguous()
+            query = (query_mask if query_mask.dtype in as_is else query_mask.to(torch.float32)).contiguous()
             C, F = mod.output_channels, mod.flag_channels
             out_mask = torch.empty((B, C, T, Hf, Wf), device=device, dtype=torch.float32)
             out_flags = torch.empty((B, T, F), device=device, dtype=torch.float32) if F > 0 else None
@@ -228,11 +261,11 @@ class SeekerEngine:
                 b1 = min(B, b0 + self.max_chunk)
                 self._run_chunk(mod, pk, frames, query[b0:b1], out_mask[b0:b1],
                                 None if out_flags is None else out_flags[b0:b1],
-                                N, T, D, P, Ho, Wo, use_cls, causal, causal_diag, queries_per_video, b0)
+                                N, T, D, P, Ho, Wo, use_cls, causal, causal_diag, queries_per_video, b0, frame_scale)
         return out_mask, out_flags
 
     def _run_chunk(self, mod, pk, frames, query, out_mask, out_flags, N, T, D, P, Ho, Wo, use_cls, causal,
-                   causal_diag, qpv=1, sample0=0):
+                   causal_diag, qpv=1, sample0=0, frame_scale=1.0):
         Bc = query.shape[0]
         M = Bc * N * T
         R = M + Bc
@@ -244,27 +277,32 @@ class SeekerEngine:
         L, G = self._launch, self._gemm
         # ---- patch embedding + embeddings (mask_tracker.py:107-108, vit.py:235-241, vision_tf.py:99-138)
         L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained), qpv, sample0,
-          nbytes=16.0 * frames[0].numel() / 3 * Bc + 2.0 * M * Kp)
+          frame_scale, nbytes=(3.0 * frames.element_size() / qpv + query.element_size()) * M * Kp / 4 + 2.0 * M * Kp)
         # ---- everything from the embeddings to the head GEMM: engine-owned buffers only -> CUDA-graph replay
         key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, self.fuse_temporal_qkv, self.fuse_ln,
                bool(mod.norm_embeddings), id(pk))
         core = lambda: self._core(mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag)
         if self.use_cuda_graph and self.profile is None:
-            hit = self._graphs.get(key)
+            with self._lock:
+                hit = self._graphs.pop(key, None)
+                if hit is not None:
+                    self._graphs[key] = hit                  # most recently used last
+                warm = self._warm.get(key, 0)
             if hit is not None:
                 hit[0].replay()
                 self.launches += hit[1]
-            elif self._warm.get(key, 0) < 1:
+            elif warm < 1:
                 core()                                   # first pass eager: kernel attributes get configured
-                self._warm[key] = 1
+                with self._lock:
+                    self._warm[key] = 1
             else:
                 n0 = self.launches
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode='thread_local'):
                     core()
-                if len(self._graphs) >= 8:
-                    self._graphs.clear()
-                self._graphs[key] = (g, self.launches - n0)
+                with self._lock:
+                    self._graphs[key] = (g, self.launches - n0, ws)   # the graph's kernels point into ws: keep it alive
+                    self._evict(self._graphs, key[0], self.max_cached_shapes)
                 g.replay()
         else:
             core()

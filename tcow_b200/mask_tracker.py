@@ -72,7 +72,21 @@ class QueryMaskTracker(torch.nn.Module):
         return self._train_engine
 
     def _wants_grad(self):
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not torch.is_grad_enabled():
+            return False
+        if any(p.requires_grad for p in self.parameters()):
+            return True
+        # nn.DataParallel replicas (train.py:223) report no parameters() (replicate() keeps the broadcast copies in
+        # _former_parameters): the autograd node of train_engine.py could not hand gradients back to the wrapped module's
+        # leaves, and the inference plan would return outputs without a grad_fn — fail here, not in loss.backward().
+        replica = getattr(self, '_is_replica', False) and any(
+            t is not None and t.requires_grad for m in self.modules() for t in getattr(m, '_former_parameters', {}).values())
+        if replica and self.training:
+            raise RuntimeError(
+                'tcow_b200.Seeker was called in gradient mode as an nn.DataParallel replica (train.py:222-223). Training '
+                'runs one process per GPU: launch with torchrun, call tcow_b200.ddp.broadcast_parameters(net) and '
+                'tcow_b200.ddp.attach(net) instead of wrapping the module in nn.DataParallel (INTEGRATION.md).')
+        return False
 
     def _forward_train(self, input_frames, query_mask, queries_per_video):
         # autograd node over the hand-written backward (train_engine.py); gradients flow to the parameters only —
@@ -83,18 +97,23 @@ class QueryMaskTracker(torch.nn.Module):
                                              query_mask, *params)
         return (mask, flags if self.flag_channels > 0 else None)
 
-    def forward(self, input_frames, query_mask):
+    def forward(self, input_frames, query_mask, frame_scale=1.0):
         '''
         :param input_frames (B, 3, T, Hf, Wf) tensor.
         :param query_mask (B, 1, T, Hf, Wf) tensor.
+        :param frame_scale (float): Extension over the reference (default = its behaviour): factor applied to the RGB
+            values on the device; 1/255 lets a caller pass the decoder's uint8 frames and skip the host-side
+            `rgb / 255.0` of data/data_plugin.py:174 (4x less host->device traffic).
         :return (output_mask (B, C, T, Hf, Wf) fp32 logits, output_flags (B, T, F) fp32 or None).
         '''
         assert query_mask.shape[1] == 1                         # mask_tracker.py:105
         if self._wants_grad():
+            if frame_scale != 1.0:
+                input_frames = input_frames.to(torch.float32) * frame_scale
             return self._forward_train(input_frames, query_mask, 1)
-        return self.engine().forward(self, input_frames, query_mask)
+        return self.engine().forward(self, input_frames, query_mask, frame_scale=frame_scale)
 
-    def forward_queries(self, input_frames, query_masks):
+    def forward_queries(self, input_frames, query_masks, frame_scale=1.0):
         '''
         All Qs queries of every clip in one pass — what pipeline.py:134-182 obtains by calling forward() Qs times
         on the same frames and stacking.  The RGB frames are uploaded / read once per clip, not once per query.
@@ -107,9 +126,12 @@ class QueryMaskTracker(torch.nn.Module):
         assert input_frames.shape[0] == B
         flat_q = query_masks.reshape(B * Qs, *query_masks.shape[2:])
         if self._wants_grad():
+            if frame_scale != 1.0:
+                input_frames = input_frames.to(torch.float32) * frame_scale
             (mask, flags) = self._forward_train(input_frames, flat_q, Qs)
         else:
-            (mask, flags) = self.engine().forward(self, input_frames, flat_q, queries_per_video=Qs)
+            (mask, flags) = self.engine().forward(self, input_frames, flat_q, queries_per_video=Qs,
+                                                  frame_scale=frame_scale)
         mask = mask.reshape(B, Qs, *mask.shape[1:])
         if flags is not None:
             flags = flags.reshape(B, Qs, *flags.shape[1:])

@@ -95,9 +95,17 @@ def cls_merge(out_cls, out, B, T, D, cls_row0, mode):
     _lib.call('tcow_cls_merge', out_cls.data_ptr(), out.data_ptr(), out.stride(0), B, T, D, cls_row0, mode, _stream())
 
 
-def patch_gather(frames, query, out, patch, normalize, queries_per_video=1, sample0=0):
-    """frames (V,3,T,H,W), query (B,1,T,H,W); sample b uses video (sample0 + b) // queries_per_video."""
-    _chk(frames, torch.float32, 'patch_gather.frames'); _chk(query, torch.float32, 'patch_gather.query')
+_DTYPE_CODE = {torch.float32: 0, torch.uint8: 1}      # TCOW_DTYPE_F32 / TCOW_DTYPE_U8
+
+
+def patch_gather(frames, query, out, patch, normalize, queries_per_video=1, sample0=0, frame_scale=1.0):
+    """frames (V,3,T,H,W), query (B,1,T,H,W), each fp32 or uint8; sample b uses video (sample0 + b) // queries_per_video.
+    RGB values are multiplied by frame_scale (1/255 for decoder-style uint8 frames, data/data_plugin.py:174)."""
+    for t, n in ((frames, 'frames'), (query, 'query')):
+        if not t.is_cuda:
+            raise RuntimeError(f'patch_gather.{n}: tensor must live on a CUDA device (tcow_b200 has no CPU path)')
+        if t.dtype not in _DTYPE_CODE:
+            raise TypeError(f'patch_gather.{n}: expected float32 or uint8, got {t.dtype}')
     _chk(out, torch.bfloat16, 'patch_gather.out')
     V, C, T, Hf, Wf = frames.shape
     B = query.shape[0]
@@ -105,8 +113,9 @@ def patch_gather(frames, query, out, patch, normalize, queries_per_video=1, samp
         raise ValueError('patch_gather: frames (V,3,T,H,W) and query (B,1,T,H,W) must be contiguous')
     if (sample0 + B - 1) // queries_per_video >= V:
         raise ValueError('patch_gather: not enough videos for the requested samples')
-    _lib.call('tcow_patch_gather', frames.data_ptr(), query.data_ptr(), out.data_ptr(), B, T, Hf, Wf, patch,
-              int(normalize), int(queries_per_video), int(sample0), _stream())
+    _lib.call('tcow_patch_gather_typed', frames.data_ptr(), _DTYPE_CODE[frames.dtype], query.data_ptr(),
+              _DTYPE_CODE[query.dtype], out.data_ptr(), B, T, Hf, Wf, patch, int(normalize), float(frame_scale),
+              int(queries_per_video), int(sample0), _stream())
     return out
 
 

@@ -14,10 +14,10 @@ class Seeker(torch.nn.Module):
         self.logger = logger
         self.seeker = mask_tracker.QueryMaskTracker(logger, **kwargs)
 
-    def forward(self, *args):
-        return self.seeker(*args)
+    def forward(self, *args, **kwargs):
+        return self.seeker(*args, **kwargs)
 
-    def forward_queries(self, input_frames, query_masks):
+    def forward_queries(self, input_frames, query_masks, frame_scale=1.0):
         '''(B,3,T,Hf,Wf), (B,Qs,1,T,Hf,Wf) -> ((B,Qs,C,T,Hf,Wf), (B,Qs,T,F)): the per-query loop of
         pipeline.py:134-182 as one batched pass over shared frames.'''
-        return self.seeker.forward_queries(input_frames, query_masks)
+        return self.seeker.forward_queries(input_frames, query_masks, frame_scale=frame_scale)

@@ -15,6 +15,7 @@ class SweepItem:
     query: int
     frame_start: int
     frame_stride: int
+    query_time: int = 0          # clip frame that carries the query mask (--seeker_query_time, data/data_utils.py:431)
 
 
 def clip_strides(num_video_frames: int, num_frames: int, query_idx: int, query_time: int = 0,
@@ -37,7 +38,7 @@ def plan_sweep(num_videos: int, num_queries: int, num_video_frames: int, num_fra
     for v in range(num_videos):
         for (start, stride) in clip_strides(num_video_frames, num_frames, query_idx, query_time):
             for q in range(num_queries):
-                items.append(SweepItem(v, q, start, stride))
+                items.append(SweepItem(v, q, start, stride, query_time))
     return items
 
 
@@ -102,7 +103,8 @@ def run_sweep(net, items: Sequence[SweepItem], get_video, get_query, get_target,
     """Run this rank's share of the evaluation sweep (eval/test.py:23-60 + pipeline.py:134-182) on `device`.
 
     get_video(v) -> (3, F, H, W) host tensor; get_query(v, q) -> (H, W) binary mask at the query frame;
-    get_target(v, q) -> (3, F, H, W) target masks or None.  Returns {(video, query, start, stride): row dict} with the
+    get_target(v, q) -> (3, F, H, W) target masks (negative = frame not annotated, data/data_plugin.py:187: such frames
+    are skipped like eval/metrics.py:21 marks them) or None.  Returns {(video, query, start, stride): row dict} with the
     per-item IoU means / counts of eval/metrics.py:43-82 (areas computed on the device by tcow_mask_iou_areas) and
     the mean flag logits."""
     import torch
@@ -133,6 +135,7 @@ def run_sweep(net, items: Sequence[SweepItem], get_video, get_query, get_target,
             part = groups[g0:g0 + clips_per_pass]
             nq = max(len(its) for _, its in part)
             rgb, qm, tg = [], [], []
+            have_target = False
             for (v, start, stride), its in part:
                 vid = video_on_device(v)
                 idx = torch.arange(num_frames, device=device) * stride + start
@@ -141,18 +144,25 @@ def run_sweep(net, items: Sequence[SweepItem], get_video, get_query, get_target,
                 for j in range(nq):
                     it = its[min(j, len(its) - 1)]            # pad ragged groups by repeating the last query
                     q = torch.zeros(1, num_frames, *vid.shape[-2:], device=device)
-                    q[0, 0] = get_query(v, it.query).to(device, non_blocking=True)
+                    q[0, it.query_time] = get_query(v, it.query).to(device, non_blocking=True)
                     qs.append(q)
                     t = target_on_device(v, it.query)
-                    ts.append(None if t is None else t.index_select(1, idx))
+                    # a (clip, query) without ground truth gets an all-negative target: every frame is then ignored
+                    ts.append(torch.full((3, num_frames, *vid.shape[-2:]), -1.0, device=device) if t is None
+                              else t.index_select(1, idx))
+                    have_target = have_target or t is not None
                 qm.append(torch.stack(qs))
-                tg.append(None if ts[0] is None else torch.stack(ts))
+                tg.append(torch.stack(ts))
             rgb_d = torch.stack(rgb)
             qm_d = torch.stack(qm)
             mask, flags = net.forward_queries(rgb_d, qm_d)                       # (Bv, Q, 3, T, H, W), (Bv, Q, T, 3)
             areas = None
-            if tg[0] is not None:
-                areas = ops.mask_iou_areas(mask.contiguous(), torch.stack(tg).contiguous())
+            if have_target:
+                tgt = torch.stack(tg).contiguous()
+                areas = ops.mask_iou_areas(mask.contiguous(), tgt)
+                # frames without annotation (any negative target pixel, eval/metrics.py:21) count as "target absent"
+                ignore = (tgt < 0).flatten(-2).any(-1)
+                areas[..., 0] = torch.where(ignore, torch.zeros_like(areas[..., 0]), areas[..., 0])
             pending.append((part, areas, None if flags is None else flags.mean(2)))
         # one device->host transfer of all per-item numbers at the end: no per-pass synchronisation
         for part, areas, flags_c in pending:

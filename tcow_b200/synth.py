@@ -103,6 +103,18 @@ def make_batch(samples, **kw):
     return torch.stack([c[0] for c in clips]), torch.stack([c[1] for c in clips])
 
 
+def bench_clips(rank, batch, num_frames=30, frame_height=240, frame_width=320, queries_per_video=3):
+    """The clips bench.py times on ``rank`` (BASELINE configs[1]): videos come with 3 queries each (README.md:42), so
+    clips form triples sharing the RGB and differing in the query.  oracle/make_golden.py runs the unmodified
+    reference on the same clips (tests/golden/full_bench_b8.npz) so the bench can check the batch it times."""
+    rgb, q = [], []
+    for i in range(batch):
+        vid = (rank * batch + i) // queries_per_video
+        rgb.append(make_clip(vid, num_frames, frame_height, frame_width)[0])
+        q.append(make_clip(1000 + rank * batch + i, num_frames, frame_height, frame_width)[1])
+    return torch.stack(rgb), torch.stack(q)
+
+
 def make_targets(samples, num_frames=30, frame_height=240, frame_width=320, output_channels=3, flag_channels=3):
     """Seeded binary mask / flag targets for the training-step parity tests and benchmark
     (stand-in for the Kubric ground truth consumed by loss.py:164-225)."""

@@ -539,7 +539,12 @@ class SeekerTrainEngine:
         g[pre + 'pos_embed'] = gv('pos')[None]
         g[pre + 'time_embed'] = gv('time')[None]
         g[pre + 'cls_token'] = gv('pos')[0].reshape(1, 1, D).clone()
-        g[pre + 'norm.weight'], g[pre + 'norm.bias'] = gv('norm_g'), gv('norm_b')
+        if mod.norm_embeddings:
+            g[pre + 'norm.weight'], g[pre + 'norm.bias'] = gv('norm_g'), gv('norm_b')
+        else:
+            # the final norm is not in the reference's graph then (vision_tf.py:152-153): its .grad stays None there, so
+            # AdamW's decoupled weight decay (train.py:233) must not see a zero gradient here either
+            g[pre + 'norm.weight'] = g[pre + 'norm.bias'] = None
         for i, w in enumerate(pk.blocks):
             p, q = f'b{i}.', pre + f'blocks.{i}.'
             for ours, theirs in (('tn1', 'temporal_norm1'), ('n1', 'norm1'), ('n2', 'norm2')):
@@ -603,5 +608,5 @@ class SeekerFunction(torch.autograd.Function):
         out = []
         for i, name in enumerate(ctx.names):
             need = ctx.needs_input_grad[6 + i]
-            out.append(grads[name] if need else None)
+            out.append(grads.get(name) if need else None)
         return (None, None, None, None, None, None, *out)

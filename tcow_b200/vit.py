@@ -8,8 +8,17 @@ implement a forward: all arithmetic runs in the CUDA engine (``tcow_b200/engine.
 """
 from __future__ import annotations
 
+import math
+import os
+from collections import OrderedDict
+
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+# File name under which torch.hub caches the ImageNet ViT-B/16 the reference downloads (vit.py:33-36); when that file is
+# already in the hub cache the reference constructs without touching the network, and so does this module.
+IMAGENET_VIT_FILE = 'jx_vit_base_p16_224-80ecf9dd.pth'
 
 
 class _NoForward(nn.Module):
@@ -111,13 +120,82 @@ class TimeSformer(_NoForward):  # vit.py:416-468
             if network_depth in (18, 24):
                 raise NotImplementedError('tcow_b200 implements network_depth=12 (ViT-B/16) only')
             raise ValueError(f'Invalid network depth {network_depth}, must be one of 12, 18, 24.')  # vit.py:449
-        if pretrained:
-            # vit.py:462-464 downloads ImageNet ViT weights; there is no network path here.
-            raise NotImplementedError('tracker_pretrained=True needs a download; construct with False and '
-                                      'load_state_dict a checkpoint (set backbone.pretrained=True for the '
-                                      'RGB normalisation of vision_tf.py:81-89)')
         self.pretrained = pretrained
         self.attention_type = attention_type
         self.drop_path_rate = drop_path_rate
         self.model = VisionTransformer(img_size, patch_size, in_chans, 768, 12, 12, 4, num_frames, causal_attention)
         self.num_patches = (img_size[0] // patch_size) * (img_size[1] // patch_size)
+        if pretrained:                                                     # vit.py:462-464
+            load_pretrained(self.model, find_pretrained_file(pretrained_model), in_chans=in_chans, patch_size=patch_size,
+                            num_frames=num_frames, num_patches=self.num_patches)
+
+
+# ------------------------------------------------------------------------------------------------ pretrained weights
+def find_pretrained_file(pretrained_model=''):
+    """Local file holding the image-ViT (or TimeSformer) weights to start from.  The reference fetches
+    jx_vit_base_p16_224 over the network when no path is given (helpers.py:109-110); there is no network path here, so
+    an explicit path, $TCOW_PRETRAINED_VIT or a copy already sitting in the torch hub cache is required."""
+    if pretrained_model:
+        if not os.path.isfile(pretrained_model):
+            raise FileNotFoundError(pretrained_model)                      # helpers.py:96-97
+        return pretrained_model
+    candidates = [os.environ.get('TCOW_PRETRAINED_VIT', ''),
+                  os.path.join(torch.hub.get_dir(), 'checkpoints', IMAGENET_VIT_FILE)]
+    for c in candidates:
+        if c and os.path.isfile(c):
+            return c
+    raise RuntimeError(
+        "tracker_pretrained is truthy but no pretrained ViT file is available offline: pass its path as "
+        f"tracker_pretrained='/path/to/{IMAGENET_VIT_FILE}', set $TCOW_PRETRAINED_VIT, or place the file in "
+        f"{candidates[1]!r}.  To evaluate a TCOW checkpoint no ImageNet weights are needed: "
+        "tcow_b200.checkpoint.build_seeker constructs without them and restores the RGB-normalisation flag.")
+
+
+def _read_weights(path):
+    """The tensors of a checkpoint file, whatever wrapper they sit in (helpers.py:22-47, :112-114)."""
+    ckpt = torch.load(path, map_location='cpu', weights_only=False)
+    if isinstance(ckpt, dict) and 'state_dict' in ckpt:
+        sd = OrderedDict((k[7:] if k.startswith('module') else k, v) for k, v in ckpt['state_dict'].items())
+    elif isinstance(ckpt, dict) and 'model_state' in ckpt:
+        sd = OrderedDict((k[6:] if k.startswith('model') else k, v) for k, v in ckpt['model_state'].items())
+    else:
+        sd = ckpt
+    return sd['model'] if 'model' in sd else sd
+
+
+@torch.no_grad()
+def load_pretrained(model, path, in_chans=4, patch_size=16, num_frames=30, num_patches=300):
+    """Inflate image-ViT weights into the divided space-time model the way helpers.py:100-202 does:
+    patch projection reshaped to a conv kernel and its 3 input channels tiled to `in_chans` (scaled by 3/in_chans);
+    classifier dropped; positional / temporal embeddings resampled (nearest) to this model's grid and length;
+    every block's temporal attention and temporal_norm1 initialised from the spatial ones unless the file has them."""
+    sd = OrderedDict(_read_weights(path))
+    key = 'patch_embed.proj.weight'
+    w = sd[key]
+    if w.dim() != 4:                                                       # vit.py:381-390: stored as a linear projection
+        w = w.reshape(w.shape[0], 3, patch_size, patch_size)
+    if in_chans != 3:
+        if w.shape[1] != 3:
+            del sd[key]                                                    # helpers.py:140-143: unusable first conv
+            w = None
+        elif in_chans == 1:
+            w = w.float().sum(1, keepdim=True).to(w.dtype)                 # helpers.py:119-133
+        else:
+            rep = int(math.ceil(in_chans / 3))
+            w = (w.float().repeat(1, rep, 1, 1)[:, :in_chans] * (3.0 / in_chans)).to(w.dtype)   # helpers.py:144-150
+    if w is not None:
+        sd[key] = w
+    sd.pop('head.weight', None)                                            # num_classes=0 here (vision_tf.py:59)
+    sd.pop('head.bias', None)
+    pos = sd['pos_embed']
+    if pos.shape[1] != num_patches + 1:                                    # helpers.py:170-178
+        grid = F.interpolate(pos[:, 1:].transpose(1, 2), size=num_patches, mode='nearest').transpose(1, 2)
+        sd['pos_embed'] = torch.cat([pos[:, :1], grid], 1)
+    if 'time_embed' in sd and sd['time_embed'].shape[1] != num_frames:     # helpers.py:180-184
+        sd['time_embed'] = F.interpolate(sd['time_embed'].transpose(1, 2), size=num_frames, mode='nearest').transpose(1, 2)
+    for k in list(sd):                                                     # helpers.py:186-202
+        if 'blocks' in k and 'attn' in k:
+            sd.setdefault(k.replace('attn', 'temporal_attn'), sd[k])
+        if 'blocks' in k and 'norm1' in k:
+            sd.setdefault(k.replace('norm1', 'temporal_norm1'), sd[k])
+    return model.load_state_dict(sd, strict=False)

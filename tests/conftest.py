@@ -35,7 +35,9 @@ def load_golden(name):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith('grad_'))
+    """Forward-pass fixtures (oracle/make_golden.py); gradient / loss / input-path / inflate fixtures have their own tests."""
+    other = ('grad_', 'pretrained_', 'loss_', 'input_', 'metrics_')
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(other))
 
 
 @pytest.fixture(scope='session')

@@ -173,3 +173,82 @@ def test_checkpoint_round_trip_in_reference_format(tmp_path, logger):
     assert open(tmp_path / 'checkpoint_epoch.txt').read().strip() == '7'
     off = dict(seeker_args, tracker_pretrained='0')
     assert checkpoint.build_seeker(logger, off).seeker.tracker_backbone.pretrained is False
+
+
+def test_pretrained_inflate_matches_reference_fixture(tmp_path, logger):
+    """tracker_pretrained=<local file>: helpers.py:100-202 (conv channels tiled 3 -> 4 and rescaled, pos_embed resampled
+    196 -> 24 patches, temporal attention / temporal_norm1 copied from the spatial ones) — digest of every backbone tensor
+    equals what the unmodified reference built from the same file (oracle/make_golden_pretrained.py)."""
+    import json
+
+    import numpy as np
+
+    from oracle import make_golden_pretrained as mgp
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'pretrained_inflate.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    path = str(tmp_path / 'vit.pth')
+    torch.save(mgp.fake_imagenet_vit(meta['seed']), path)
+    net = tcow_b200.Seeker(logger, tracker_pretrained=path, **meta['kwargs'])
+    assert net.seeker.tracker_pretrained is True and net.seeker.tracker_backbone.pretrained is True
+    got = mgp.backbone_digests(net.state_dict())
+    want = {k.replace('/', '.'): z[k] for k in z.files if k != 'meta'}
+    assert set(got) == set(want) and len(got) == 247
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    # the projection may be stored as a linear layer (vit.py:381-390): same result
+    torch.save(mgp.fake_imagenet_vit(meta['seed'], linear_patch_proj=True), path)
+    net2 = tcow_b200.Seeker(logger, tracker_pretrained=path, **meta['kwargs'])
+    assert torch.equal(net2.state_dict()[mgp.PREFIX + 'patch_embed.proj.weight'],
+                       net.state_dict()[mgp.PREFIX + 'patch_embed.proj.weight'])
+
+
+def test_pretrained_without_a_file_fails_loudly(logger, monkeypatch, tmp_path):
+    monkeypatch.delenv('TCOW_PRETRAINED_VIT', raising=False)
+    monkeypatch.setattr(torch.hub, 'get_dir', lambda: str(tmp_path))
+    with pytest.raises(RuntimeError, match='offline'):
+        tcow_b200.Seeker(logger, **{**KW, 'tracker_pretrained': '1'})       # args.py:150 default, no network here
+    with pytest.raises(FileNotFoundError):
+        tcow_b200.Seeker(logger, **{**KW, 'tracker_pretrained': str(tmp_path / 'missing_file.pth')})
+
+
+def _as_data_parallel_replica(module):
+    """What torch.nn.parallel.replicate leaves on a device: no _parameters, broadcast copies in _former_parameters."""
+    memo = {}
+    for m in module.modules():
+        r = m._replicate_for_data_parallel()
+        r._former_parameters = {}
+        memo[m] = r
+    for m, r in memo.items():
+        for k, child in m._modules.items():
+            r._modules[k] = memo[child] if child is not None else None
+        for k, p in m._parameters.items():
+            if p is not None:
+                t = p * 1.0                      # non-leaf copy that still requires grad, like Broadcast.apply's output
+                setattr(r, k, t)
+                r._former_parameters[k] = t
+    return memo[module]
+
+
+def test_data_parallel_replica_in_grad_mode_names_the_ddp_route(net):
+    rep = _as_data_parallel_replica(net.seeker)
+    assert len(list(rep.parameters())) == 0
+    rgb, q = synth.make_batch([0], num_frames=4, frame_height=32, frame_width=48)
+    rep.train()
+    with pytest.raises(RuntimeError, match='ddp.attach'):
+        rep(rgb, q)
+    rep.eval()                                   # inference replicas are fine (they fail later only for lack of a GPU)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        rep(rgb, q)
+    # the weight-cache stamp sees the replica's tensors (a stale stamp would mean stale packed weights)
+    assert len(SeekerEngine._stamp(rep)) == len(SeekerEngine._stamp(net.seeker)) > 0
+
+
+def test_ddp_broadcast_bumps_the_version_stamp(net):
+    """ddp.broadcast_parameters writes through p.detach() (shares the version counter), not p.data."""
+    p = next(net.parameters())
+    v0 = p._version
+    with torch.no_grad():
+        p.detach().copy_(p.detach() + 0)
+    assert p._version == v0 + 1
+    src = open(os.path.join(ROOT, 'tcow_b200', 'ddp.py')).read()
+    assert 'dist.broadcast(p.data' not in src

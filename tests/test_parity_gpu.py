@@ -242,3 +242,43 @@ def test_sweep_runner_matches_per_item_forwards(logger):
     a = ops.mask_iou_areas(mask.contiguous(), tgt[:, idx][None].to(DEV).contiguous()).cpu()[0]
     assert torch.equal(a[..., 0], gt.sum((-1, -2)).float()) and torch.equal(a[..., 1], (pred & gt).sum((-1, -2)).float())
     assert torch.equal(a[..., 2], (pred | gt).sum((-1, -2)).float())
+
+
+def test_timed_bench_batch_matches_reference_golden(logger):
+    """The exact batch bench.py times (BASELINE configs[1]: 8 clips in one pass, M = 72 000 rows, CTA-pair GEMMs): clips 0
+    and 7 against the unmodified reference's outputs on the same clips (tests/golden/full_bench_b8.npz)."""
+    meta, gmask, gflags = load_golden('full_bench_b8')
+    net = build(logger, meta)
+    rgb, q = synth.bench_clips(0, meta['bench_batch'], 30, 240, 320)
+    with torch.no_grad():
+        mask, flags = net(rgb.cuda(), q.cuda())
+    ly, lx = meta['lattice']
+    m = mask[meta['samples']].cpu()[:, :, :, ::ly, ::lx]
+    err = (m - gmask).abs().max().item()
+    ious = [iou(m[s], gmask[s]) for s in range(m.shape[0])]
+    print(f'bench batch: max|dlogit| {err:.4e}  IoU {ious}')
+    assert err <= TOL_LOGIT and min(ious) >= TOL_IOU
+    assert (flags[meta['samples']].cpu() - gflags).abs().max().item() <= 2e-2
+
+
+def test_uint8_inputs_with_device_side_scaling(logger):
+    """decoder-style uint8 frames / query masks go straight into the gather kernel.  frame_scale=1/255
+    reproduces the host-side `rgb / 255.0` of data/data_plugin.py:174; without it uint8 is the plain cast of
+    mask_tracker.py:103 (bit-identical to passing .float())."""
+    meta, gmask, _ = load_golden('mid_causal1')
+    net = build(logger, meta)
+    rgb, q = synth.make_batch(meta['samples'], num_frames=meta['T'], frame_height=meta['Hf'], frame_width=meta['Wf'],
+                              query_frame=meta['query_frame'])
+    rgb8 = (rgb * 255).round().to(torch.uint8)
+    with torch.no_grad():
+        m8, f8 = net(rgb8.cuda(), q.to(torch.uint8).cuda(), frame_scale=1.0 / 255.0)
+        mf, ff = net((rgb8.float() / 255.0).cuda(), q.cuda())
+        mq, fq = net.forward_queries(rgb8.cuda(), q.to(torch.uint8).cuda()[:, None], frame_scale=1.0 / 255.0)
+        raw8, _ = net(rgb8.cuda(), q.cuda())
+        rawf, _ = net(rgb8.float().cuda(), q.cuda())
+    assert (m8 - mf).abs().max().item() <= 2e-3 and (f8 - ff).abs().max().item() <= 2e-3   # x*(1/255) vs x/255 roundings
+    assert torch.equal(mq[:, 0], m8) and torch.equal(fq[:, 0], f8)
+    assert torch.equal(raw8, rawf)
+    ly, lx = meta['lattice']
+    # quantising the frames to 8 bits moves the logits by less than the bf16 budget: still within tolerance of the golden
+    assert (m8.cpu()[:, :, :, ::ly, ::lx] - gmask).abs().max().item() <= TOL_LOGIT
