@@ -65,7 +65,13 @@ def our_grads(net, rgb, q, tm, tf):
     loss = synth.training_loss(mask, flags, tm.to(DEV), None if flags is None else tf.to(DEV))
     loss.backward()
     torch.cuda.synchronize()
-    return float(loss.detach()), {n: p.grad for n, p in net.named_parameters()}, mask.detach()
+    # parameters outside the graph keep .grad = None, exactly as under the reference's autograd: the final norm when
+    # norm_embeddings is off (vision_tf.py:152-153) — an optimizer with weight decay must skip it (train.py:233)
+    unused = {n for n, p in net.named_parameters() if p.grad is None}
+    final_norm = {synth.BACKBONE_PREFIX + 'norm.weight', synth.BACKBONE_PREFIX + 'norm.bias'}
+    assert unused == (set() if net.seeker.norm_embeddings else final_norm), unused
+    grads = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in net.named_parameters()}
+    return float(loss.detach()), grads, mask.detach()
 
 
 @pytest.mark.parametrize('name', GRAD_CASES)
@@ -124,18 +130,20 @@ def test_query_loop_then_one_backward_and_accumulation(logger):
     outs = [net(rgb, qq) for qq in (q0, q1)]                      # two forwards alive at once
     loss = synth.training_loss(torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs]), tm, tf)
     loss.backward()
-    g_loop = {n: p.grad.clone() for n, p in net.named_parameters()}
+    g_loop = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
     net.zero_grad(set_to_none=True)
     mask, flags = net.forward_queries(rgb, torch.stack([q0, q1], 1))
     synth.training_loss(mask[0], flags[0], tm, tf).backward()
-    g_batched = {n: p.grad.clone() for n, p in net.named_parameters()}
+    g_batched = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    assert set(g_batched) == set(g_loop) and len(g_loop) == 249
     for n in g_loop:
         d = (g_loop[n] - g_batched[n]).norm().item()
         assert d <= 2e-2 * g_loop[n].norm().item() + 1e-9, n
     mask, flags = net.forward_queries(rgb, torch.stack([q0, q1], 1))
     synth.training_loss(mask[0], flags[0], tm, tf).backward()   # accumulates
     for n, p in net.named_parameters():
-        assert (p.grad - 2 * g_batched[n]).norm().item() <= 1e-3 * g_batched[n].norm().item() + 1e-9, n
+        if n in g_batched:
+            assert (p.grad - 2 * g_batched[n]).norm().item() <= 1e-3 * g_batched[n].norm().item() + 1e-9, n
 
 
 def test_optimizer_step_reduces_loss_and_repacks_weights(logger):
