@@ -118,6 +118,19 @@ int tcow_patch_gather_typed(const void* frames, int frames_dtype, const void* qu
                             int T, int Hf, int Wf, int patch, int normalize, float frame_scale, int queries_per_video,
                             int sample0, void* stream);
 
+/* Input path: a decoder-layout uint8 video [F,H,W,C] -> the clip tensor the reference's loader builds on
+ * the host, in one pass on the device: frame t = video frame frame_start + t*frame_stride (data/data_plugin.py:156-157),
+ * `/ 255.0` (:174), window (y0,x0,h,w) = the centre crop to the target aspect ratio and optional crop rectangle of
+ * data/augs.py:170-196 (flip != 0 mirrors the window horizontally first, :189-190), resized to Hf x Wf exactly as
+ * torchvision Resize does (:198-206) and written channel-first [C,T,Hf,Wf] (data_plugin.py:199-201).
+ * tcow_clip_from_video_u8: antialiased bilinear (ATen's separable triangle filter, align_corners=False), fp32 out in [0,1].
+ * tcow_mask_clip_from_video_u8: legacy 'nearest' (src = floor(dst * in/out)), uint8 out — query / target masks. */
+int tcow_clip_from_video_u8(const uint8_t* video, int F, int H, int W, int C, int frame_start, int frame_stride, int T,
+                            int y0, int x0, int h, int w, int flip, int Hf, int Wf, float* out, void* stream);
+int tcow_mask_clip_from_video_u8(const uint8_t* video, int F, int H, int W, int C, int frame_start, int frame_stride,
+                                 int T, int y0, int x0, int h, int w, int flip, int Hf, int Wf, uint8_t* out,
+                                 void* stream);
+
 /* Residual-stream initialisation (vision_tf.py:99-138): X[(b*N+n)*T+t,:] = conv_bias + pos_embed[1+n] +
  * time_embed[t];  X[M+b,:] = cls_token + pos_embed[0].  The patch GEMM then accumulates into X. */
 int tcow_embed_init(float* X, const float* conv_bias, const float* pos_embed, const float* time_embed,
