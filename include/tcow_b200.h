@@ -163,6 +163,36 @@ int tcow_mask_loss_sums(const float* logits, const float* target, const float* w
 int tcow_mask_loss_grad(const float* logits, const float* target, const float* weights, int64_t n, const float* coef,
                         float* grad, void* stream);
 
+/* The reference's complete mask loss (loss.py:164-225 my_mask_loss) over a (B,Q,T,H,W) slice addressed in place as
+ * G = B*Q groups of T frames of hw pixels (element (g,t,p) at base + g*group_stride + t*hw + p; hw % 4 == 0):
+ *   frames whose weights are all zero are skipped (which_frames, :176-185); l = BCE-with-logits or sigmoid focal loss
+ *   (focal != 0; :50-53); custom = mean(w*l); bootstrap = mean of the top int(topk_frac*N) values of l' (:12-16; exact
+ *   radix select on the device, l' = w*l if weighted_aot else l); jaccard = Tversky(alpha,beta,eps) (:19-31) or the
+ *   bootstrap term itself when weighted_aot (:205); loss = sqrt(selected/total frames) * (aot*(bootstrap+jaccard)/2 +
+ *   (1-aot)*custom), or 0 when nothing is selected / mean(w) < 1e-4 (:187,:221).
+ * forward writes the scalar loss (device fp32), the per-frame selection flags [G*T] and the `state` block
+ * (tcow_mask_loss_state_bytes() bytes) that backward consumes: grad (=|+=) upstream * dloss/dlogits, same addressing. */
+int64_t tcow_mask_loss_state_bytes(void);
+int tcow_mask_loss_forward(const float* logits, int64_t gs_x, const float* target, int64_t gs_y, const float* weights,
+                           int64_t gs_w, int G, int T, int64_t hw, int focal, int weighted_aot, double aot_loss,
+                           double topk_frac, double alpha, double beta, double eps, uint8_t* frame_sel, void* state,
+                           float* loss_out, void* stream);
+int tcow_mask_loss_backward(const float* logits, int64_t gs_x, const float* target, int64_t gs_y, const float* weights,
+                            int64_t gs_w, int G, int T, int64_t hw, int focal, int weighted_aot, const uint8_t* frame_sel,
+                            const void* state, const float* upstream, float* grad, int64_t gs_g, int accumulate,
+                            void* stream);
+
+/* Per-pixel loss weights (loss.py:83-148 get_mask_track_pixel_weights, times the per-frame weights of :55-81):
+ *   counts[0..1] = #(target == 1), #(target == 0)                                   (class balancing statistics, :103-107)
+ *   out = frame_w[f] * (corr[0] if target == 1, corr[1] if target == 0) * (2 if occl != 0) * (hard_negative_factor if the
+ *         pixel is within band/2 of a target > 0 pixel (reflect padding — what gaussian_blur(...) > 0 amounts to, :133-146)
+ *         and target < 0.5).   corr: device fp32[2] = (pos_corr, neg_corr) or NULL; occl, frame_w may be NULL;
+ *   tmp: G*T*H*W bytes of scratch (needed when hard_negative_factor > 1); band odd. */
+int tcow_loss_class_counts(const float* target, int64_t gs_t, int G, int T, int64_t hw, uint64_t* counts, void* stream);
+int tcow_loss_pixel_weights(const float* target, int64_t gs_t, const uint8_t* occl, int64_t gs_o, const float* frame_w,
+                            const float* corr, int G, int T, int H, int W, float hard_negative_factor, int band,
+                            uint8_t* tmp, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training step (BASELINE configs[3]: fwd+bwd, data-parallel).  The reference gets its backward from torch.autograd
  * over the modules cited above (train.py:93-101 loss.backward(); optimizer.step()); these entry points are the

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TCOW_B200_LIB selects an alternative build of the same ABI (A/B experiments); default is the in-tree library.
@@ -46,6 +46,14 @@ SIGNATURES = {
     'tcow_mask_loss_workspace_floats': [],
     'tcow_mask_loss_sums': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     'tcow_mask_loss_grad': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    'tcow_mask_loss_state_bytes': [],
+    'tcow_mask_loss_forward': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_int, c_int,
+                               c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p],
+    'tcow_mask_loss_backward': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    'tcow_loss_class_counts': [c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p],
+    'tcow_loss_pixel_weights': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                c_int, c_void_p, c_void_p, c_void_p],
     # ---- training step
     'tcow_gemm_bf16_aux': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                            c_int, c_int, c_int, c_int, c_void_p],
@@ -92,7 +100,8 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = (c_char_p if name == 'tcow_last_error' else
-                          c_int64 if name in ('tcow_train_workspace_floats', 'tcow_mask_loss_workspace_floats') else c_int)
+                          c_int64 if name in ('tcow_train_workspace_floats', 'tcow_mask_loss_workspace_floats',
+                                              'tcow_mask_loss_state_bytes') else c_int)
         _lib = lib
     return _lib
 
