@@ -358,8 +358,10 @@ extern "C" int tcow_attn_spatial(const void* qkv, int64_t ld_qkv, void* out, int
   static const char impl = [] { const char* e = getenv("TCOW_SPATIAL_IMPL"); return e ? e[0] : '\0'; }();
   const bool force_mma = impl == 'm';
   if (!force_mma && (ld_qkv % 8) == 0) {
-    if (S <= 304 && impl != 's')
+    if (S <= 304 && impl == 'r')   // round-1 resident kernel (two CTAs per SM), kept for A/B timing
       return launch_spatial_tc(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
+    if (S <= 304 && impl != 's')
+      return launch_spatial_pp(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
     return launch_spatial_stream(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
   }
   // pick the query-block width that wastes the fewest padded query rows (ties -> wider block)
@@ -377,7 +379,11 @@ extern "C" int tcow_attn_spatial_train(const void* qkv, int64_t ld_qkv, void* ou
   if ((ld_qkv % 8) || (ld_out % 8)) return set_error(TCOW_ERR_ARG, "attn_spatial_train: row pitches must be multiples of 8");
   if (N + (use_cls ? 1 : 0) > 304)
     return set_error(TCOW_ERR_ARG, "attn_spatial_train: %d tokens per frame > 304 not supported in training", N + (use_cls ? 1 : 0));
-  return launch_spatial_tc(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0,
+  static const char impl = [] { const char* e = getenv("TCOW_SPATIAL_IMPL"); return e ? e[0] : '\0'; }();
+  if (impl == 'r')
+    return launch_spatial_tc(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0,
+                             static_cast<cudaStream_t>(stream), lse);
+  return launch_spatial_pp(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0,
                            static_cast<cudaStream_t>(stream), lse);
 }
 

@@ -35,7 +35,8 @@ for _ in range(reps):
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(10):
+ITERS = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+for _ in range(ITERS):
     if op == 'spatial':
         ops.attn_spatial(qkv, out, ocls, B, N, T, H, True, M)
     elif op == 'temporal':
@@ -44,4 +45,4 @@ for _ in range(10):
         ops.qkv_temporal_attn(a_, wq, bq, out, B * N, T, H, 0)
 e1.record()
 torch.cuda.synchronize()
-print(op, 'avg us', e0.elapsed_time(e1) * 100)
+print(op, os.path.basename(os.environ.get('TCOW_B200_LIB', 'default')), 'avg us', e0.elapsed_time(e1) * 1000 / ITERS)
