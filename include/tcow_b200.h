@@ -118,6 +118,17 @@ int tcow_patch_gather_typed(const void* frames, int frames_dtype, const void* qu
                             int T, int Hf, int Wf, int patch, int normalize, float frame_scale, int queries_per_video,
                             int sample0, void* stream);
 
+/* The whole patch embedding as ONE kernel (north_star bullet 1): query mask as 4th channel (mask_tracker.py:103-108), RGB
+ * scale / normalisation (vision_tf.py:81-89), Conv2d(4, D, 16, 16) as an implicit tcgen05 GEMM (vit.py:233-241; weight
+ * [D, 4*16*16] bf16, K = c*256 + r*16 + w) and the embeddings of vision_tf.py:99-138 written into the fp32 stream:
+ *   X[(b*N+n)*T+t, :] = conv + conv_bias + pos_embed[1+n] + time_embed[t];   X[M+b, :] = cls_token + pos_embed[0].
+ * Arguments as tcow_patch_gather_typed; requires patch 16, D % 256 == 0 (TCOW_ERR_ARG otherwise: callers fall
+ * back to tcow_patch_gather_typed + tcow_embed_init + tcow_gemm_bf16). */
+int tcow_patch_embed_fused(const void* frames, int frames_dtype, const void* query, int query_dtype, const void* weight,
+                           const float* conv_bias, const float* pos_embed, const float* time_embed, const float* cls_token,
+                           float* X, int B, int T, int Hf, int Wf, int patch, int D, int normalize, float frame_scale,
+                           int queries_per_video, int sample0, void* stream);
+
 /* Input path: a decoder-layout uint8 video [F,H,W,C] -> the clip tensor the reference's loader builds on
  * the host, in one pass on the device: frame t = video frame frame_start + t*frame_stride (data/data_plugin.py:156-157),
  * `/ 255.0` (:174), window (y0,x0,h,w) = the centre crop to the target aspect ratio and optional crop rectangle of

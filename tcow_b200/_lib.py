@@ -38,6 +38,8 @@ SIGNATURES = {
                                 c_int, c_int, c_void_p, c_void_p],
     'tcow_mask_clip_from_video_u8': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_void_p, c_void_p],
+    'tcow_patch_embed_fused': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p],
     'tcow_embed_init': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'tcow_mask_upsample': [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                            c_void_p],

@@ -51,6 +51,9 @@ class SeekerEngine:
         # the stand-alone kernel's memory parallelism, and the row-unit tile order it needs costs the K=3072 GEMM 17 %.
         # Off by default (TCOW_FUSE_LN=1 enables; profiles/r01_notes.md).
         self.fuse_ln = os.environ.get('TCOW_FUSE_LN', '0') == '1'
+        # Patch embedding as one kernel (gather + implicit GEMM + embeddings, csrc/patch_embed_fused.cu) whenever the shape
+        # allows it (patch 16, T <= 32); TCOW_FUSE_PATCH=0 forces the three-kernel form (gather, embed_init, reduce-add GEMM).
+        self.fuse_patch_embed = os.environ.get('TCOW_FUSE_PATCH', '1') != '0'
         self._lock = threading.Lock()
         self._packed = {}      # device index -> (stamp, _Packed)
         self._workspace = {}   # (device index, Bc, shape key) -> dict of tensors
@@ -276,12 +279,20 @@ class SeekerEngine:
         PM = ws['H'][:M * Kp].view(M, Kp)
         L, G = self._launch, self._gemm
         # ---- patch embedding + embeddings (mask_tracker.py:107-108, vit.py:235-241, vision_tf.py:99-138)
-        L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained), qpv, sample0,
-          frame_scale, nbytes=(3.0 * frames.element_size() / qpv + query.element_size()) * M * Kp / 4 + 2.0 * M * Kp)
+        fused_embed = (self.fuse_patch_embed and P == 16 and T <= ops.PATCH_EMBED_FUSED_MAX_T and D % 256 == 0
+                       and not self.fuse_ln)
+        in_bytes = (3.0 * frames.element_size() / qpv + query.element_size()) * M * Kp / 4
+        if fused_embed:
+            L('patch_embed', ops.patch_embed_fused, frames, query, pk.patch_w, pk.patch_b, pk.pos, pk.time, pk.cls, X, P,
+              bool(mod.tracker_backbone.pretrained), qpv, sample0, frame_scale, flops=2.0 * M * D * Kp,
+              nbytes=in_bytes + 4.0 * R * D)
+        else:
+            L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained), qpv, sample0,
+              frame_scale, nbytes=in_bytes + 2.0 * M * Kp)
         # ---- everything from the embeddings to the head GEMM: engine-owned buffers only -> CUDA-graph replay
         key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, self.fuse_temporal_qkv, self.fuse_ln,
-               bool(mod.norm_embeddings), id(pk))
-        core = lambda: self._core(mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag)
+               bool(mod.norm_embeddings), id(pk), fused_embed)
+        core = lambda: self._core(mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag, fused_embed)
         if self.use_cuda_graph and self.profile is None:
             with self._lock:
                 hit = self._graphs.pop(key, None)
@@ -312,12 +323,13 @@ class SeekerEngine:
         if out_flags is not None:
             L('flag_mean', ops.flag_mean, LOW, out_flags, Bc, N, T, mod.flag_channels, pk.flag_col0)
 
-    def _core(self, mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag):
+    def _core(self, mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag, fused_embed=False):
         X, A, QKV, O, OCLS, LOW = ws['X'], ws['A'], ws['QKV'], ws['O'], ws['OCLS'], ws['LOW']
         H = ws['H'][:R * 4 * D].view(R, 4 * D)
         PM = ws['H'][:M * Kp].view(M, Kp)
         L, G = self._launch, self._gemm
-        L('embed_init', ops.embed_init, X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D, nbytes=4.0 * R * D)
+        if not fused_embed:
+            L('embed_init', ops.embed_init, X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D, nbytes=4.0 * R * D)
         Rs = R if use_cls else M
         ln_bytes = lambda rows: 6.0 * rows * D
         fuse_ln = self.fuse_ln
@@ -334,7 +346,10 @@ class SeekerEngine:
                 L('ln', ops.layernorm, X[:ln_rows], ln_params[0], ln_params[1], A[:ln_rows], nbytes=ln_bytes(ln_rows))
 
         nblk = len(pk.blocks)
-        residual('gemm_patch', PM, (pk.patch_w, None), M, pk.blocks[0].tn1, M)   # + temporal_norm1 of block 0
+        if fused_embed:     # X already holds the embedded tokens: only temporal_norm1 of block 0 remains
+            L('ln', ops.layernorm, X[:M], pk.blocks[0].tn1[0], pk.blocks[0].tn1[1], A[:M], nbytes=ln_bytes(M))
+        else:
+            residual('gemm_patch', PM, (pk.patch_w, None), M, pk.blocks[0].tn1, M)   # + temporal_norm1 of block 0
         for bi, w in enumerate(pk.blocks):
             # temporal attention + temporal_fc + residual (vit.py:169-176); cls rows untouched.  A = LN_tn1(X[:M]).
             if self.fuse_temporal_qkv:

@@ -119,6 +119,37 @@ def patch_gather(frames, query, out, patch, normalize, queries_per_video=1, samp
     return out
 
 
+PATCH_EMBED_FUSED_MAX_T = 1 << 20     # no limit on the frame count (kept for callers that gate on it)
+
+
+def patch_embed_fused(frames, query, weight, conv_bias, pos_embed, time_embed, cls_token, X, patch, normalize,
+                      queries_per_video=1, sample0=0, frame_scale=1.0):
+    """X[:M] = conv(cat(frames, query)) + conv_bias + pos_embed[1+n] + time_embed[t]; X[M:M+B] = cls_token + pos_embed[0] —
+    gather, GEMM and embeddings in one kernel (patch 16, D % 256 == 0)."""
+    for t, n in ((frames, 'frames'), (query, 'query')):
+        if not t.is_cuda:
+            raise RuntimeError(f'patch_embed_fused.{n}: tensor must live on a CUDA device (tcow_b200 has no CPU path)')
+        if t.dtype not in _DTYPE_CODE:
+            raise TypeError(f'patch_embed_fused.{n}: expected float32 or uint8, got {t.dtype}')
+    _chk(weight, torch.bfloat16, 'patch_embed_fused.weight'); _chk(X, torch.float32, 'patch_embed_fused.X')
+    V, C, T, Hf, Wf = frames.shape
+    B = query.shape[0]
+    D = weight.shape[0]
+    N = (Hf // patch) * (Wf // patch)
+    if C != 3 or tuple(query.shape) != (B, 1, T, Hf, Wf) or not (frames.is_contiguous() and query.is_contiguous()):
+        raise ValueError('patch_embed_fused: frames (V,3,T,H,W) and query (B,1,T,H,W) must be contiguous')
+    if (sample0 + B - 1) // queries_per_video >= V:
+        raise ValueError('patch_embed_fused: not enough videos for the requested samples')
+    if tuple(weight.shape) != (D, 4 * patch * patch) or not weight.is_contiguous() or not X.is_contiguous() \
+            or X.shape[0] < B * N * T + B or X.shape[1] != D:
+        raise ValueError('patch_embed_fused: weight [D, 4*P*P] and X [>= M+B, D] must be contiguous')
+    _lib.call('tcow_patch_embed_fused', frames.data_ptr(), _DTYPE_CODE[frames.dtype], query.data_ptr(),
+              _DTYPE_CODE[query.dtype], weight.data_ptr(), conv_bias.data_ptr(), pos_embed.data_ptr(), time_embed.data_ptr(),
+              cls_token.data_ptr(), X.data_ptr(), B, T, Hf, Wf, patch, D, int(normalize), float(frame_scale),
+              int(queries_per_video), int(sample0), _stream())
+    return X
+
+
 def embed_init(X, conv_bias, pos_embed, time_embed, cls_token, B, N, T, D):
     _lib.call('tcow_embed_init', X.data_ptr(), conv_bias.data_ptr(), pos_embed.data_ptr(), time_embed.data_ptr(),
               cls_token.data_ptr(), B, N, T, D, _stream())

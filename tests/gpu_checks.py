@@ -225,6 +225,42 @@ def check_patch_gather(B, T, Hf, Wf, normalize):
         f'patch_gather B={B} T={T} {Hf}x{Wf} norm={normalize}'
 
 
+def check_patch_embed_fused(B, T, Hf, Wf, normalize, u8=False, qpv=1):
+    """One-kernel patch embedding vs the three reference steps in fp32 torch (bf16-rounded operands, as the GEMM sees them):
+    cat(frames, query) -> (optional normalisation) -> conv2d k=s=16 -> + bias + pos_embed[1+n] + time_embed[t]; cls rows."""
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(14)
+    P, D = 16, 768
+    V = (B + qpv - 1) // qpv
+    fr = torch.rand(V, 3, T, Hf, Wf, device=d, generator=g)
+    q = (torch.rand(B, 1, T, Hf, Wf, device=d, generator=g) > 0.7).float()
+    scale = 1.0
+    if u8:
+        fr = (fr * 255).round().to(torch.uint8)
+        q = q.to(torch.uint8)
+        scale = 1.0 / 255.0
+    Ho, Wo = Hf // P, Wf // P
+    N = Ho * Wo
+    M = B * N * T
+    w = (torch.randn(D, 4 * P * P, device=d, generator=g) * 0.03).to(torch.bfloat16)
+    cb, pos, tim, cls = (torch.randn(sh, device=d, generator=g) * 0.1 for sh in [(D,), (N + 1, D), (T, D), (D,)])
+    X = torch.full((M + B, D), float('nan'), device=d)
+    ops.patch_embed_fused(fr, q, w, cb, pos, tim, cls, X, P, normalize, qpv, 0, scale)
+    torch.cuda.synchronize()
+    f2 = fr.float() * scale
+    if normalize:
+        f2 = (f2 - 0.45) / 0.225
+    f2 = f2[(torch.arange(B, device=d) // qpv)]
+    x4 = torch.cat([f2, q.float()], 1).to(torch.bfloat16).float()
+    pm = x4.reshape(B, 4, T, Ho, P, Wo, P).permute(0, 3, 5, 2, 1, 4, 6).reshape(M, 4 * P * P)
+    ref = pm @ w.float().t() + (cb[None, None, None] + pos[None, 1:, None] + tim[None, None]).expand(B, N, T, D).reshape(M, D)
+    err = (X[:M] - ref).abs().max().item()
+    err_cls = (X[M:] - (cls + pos[0])[None]).abs().max().item()
+    if not torch.isfinite(X).all():
+        return float('inf'), 0.0, 'patch_embed_fused left rows unwritten'
+    return max(err, err_cls), 2e-3, f'patch_embed_fused B={B} T={T} {Hf}x{Wf} norm={normalize} u8={u8} qpv={qpv} (cls {err_cls:.1e})'
+
+
 def check_embed_init(B, N, T, D=768):
     d = _dev()
     g = torch.Generator(device=d).manual_seed(5)
@@ -321,6 +357,11 @@ ALL_CHECKS = [
     ('patch_gather', lambda: check_patch_gather(2, 3, 32, 48, False)),
     ('patch_gather_norm', lambda: check_patch_gather(1, 2, 240, 320, True)),
     ('embed_init', lambda: check_embed_init(2, 6, 4)),
+    ('patch_embed_fused', lambda: check_patch_embed_fused(2, 3, 32, 48, False)),
+    ('patch_embed_fused_norm_u8', lambda: check_patch_embed_fused(1, 2, 240, 320, True, u8=True)),
+    ('patch_embed_fused_ragged_qpv', lambda: check_patch_embed_fused(3, 30, 64, 96, False, qpv=3)),
+    ('patch_embed_fused_full', lambda: check_patch_embed_fused(8, 30, 240, 320, False, u8=True, qpv=3)),
+    ('patch_embed_fused_T60_1200', lambda: check_patch_embed_fused(1, 60, 480, 640, False)),
     ('mask_upsample_bilinear', lambda: check_mask_upsample(2, 3, 15, 20, 4, 0)),
     ('mask_upsample_nearest', lambda: check_mask_upsample(1, 2, 2, 3, 4, 1)),
     ('mask_upsample_stride2', lambda: check_mask_upsample(1, 2, 2, 3, 2, 0)),
