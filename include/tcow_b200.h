@@ -233,6 +233,11 @@ int tcow_scale_rows_bf16(const void* x, int64_t ldx, const float* scale, void* o
  * N1, N2 multiples of 64. */
 int tcow_gemm_bf16_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, int R, int N1,
                          int N2, void* stream);
+/* The same weight gradient plus the bias gradient of the layer in the same pass: db[n1] (fp32, N1 entries) += sum over the
+ * R rows of A[:, n1] — the column sums come out of the dY tiles the MMA already has in shared memory (replaces a separate
+ * tcow_colsum_bf16 pass).  db == NULL: exactly tcow_gemm_bf16_wgrad. */
+int tcow_gemm_bf16_wgrad_bias(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, float* db,
+                              int R, int N1, int N2, void* stream);
 
 /* Floats of scratch the reductions below need (LayerNorm-backward / column-sum / time-embedding partial sums). */
 int64_t tcow_train_workspace_floats(int max_cols);

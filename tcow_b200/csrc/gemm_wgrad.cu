@@ -50,7 +50,8 @@ __host__ __device__ constexpr uint32_t wg_idesc(int M, int N) {
 template <int BN, int CL>
 __global__ void __launch_bounds__(WgCfg<BN, CL>::THREADS, 1)
 gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ CUtensorMap tmC, int R, int N1, int N2, int splits, int kb_per_split) {
+                       const __grid_constant__ CUtensorMap tmC, int R, int N1, int N2, int splits, int kb_per_split,
+                       float* __restrict__ db) {
   using Cfg = WgCfg<BN, CL>;
   constexpr int CS = CL;
   constexpr int STAGES = Cfg::STAGES;
@@ -92,7 +93,9 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CS);  // multicast mode: both CTAs must have drained the stage before either refills it
+      // multicast mode: both CTAs must have drained the stage before either refills it; bias-gradient mode: so must the
+      // two column-sum warps
+      mbar_init(empty_bar(s), CS + (db ? 2 : 0));
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -163,6 +166,41 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         __syncwarp();
       }
     }
+  } else if (warp <= 3 && db != nullptr) {
+    // ------------------------------------------------ bias gradient: db[n1] += sum over the token rows of dY[:, n1]
+    // (nn.Linear bias, vit.py:50-52,73-74).  The dY tile of every stage is already in shared memory for the MMA: warps 2-3
+    // add up its 64 rows (thread = two adjacent columns of the 128) for the units of column tile 0 — every n2 tile of a
+    // split streams the same dY rows — instead of a separate pass over dY (tcow_colsum_bf16: 84 launches per step).
+    const int tcol = (warp - 2) * 32 + lane;                        // columns 2*tcol, 2*tcol+1 of the tile
+    const uint32_t col_off = (tcol >> 5) * (WG_BK * 128) + ((tcol & 3) << 2);   // 64-column block, word inside the 16-B chunk
+    const uint32_t chunk = (tcol & 31) >> 2;
+    uint32_t it = 0;
+    for (int u = unit0; u < units; u += unit_step) {
+      int m_blk, n_blk, kb0, kb1;
+      unit_at(u, m_blk, n_blk, kb0, kb1);
+      float s0 = 0.f, s1 = 0.f;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full_bar(s), (it / STAGES) & 1);
+        if (n_blk == 0) {
+          const uint32_t sa = base + s * Cfg::STAGE_BYTES + col_off;
+#pragma unroll 8
+          for (int r = 0; r < WG_BK; ++r) {
+            uint32_t v;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sa + r * 128 + ((chunk ^ (r & 7)) << 4)));
+            s0 += __uint_as_float(v << 16);
+            s1 += __uint_as_float(v & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
+      }
+      if (n_blk == 0) {
+        const int c0 = m_blk * WG_BM + 2 * tcol;
+        if (c0 < N1) atomicAdd(db + c0, s0);
+        if (c0 + 1 < N1) atomicAdd(db + c0 + 1, s1);
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue: TMEM -> staging -> TMA reduce-add into dW
     const int ew = warp & 3;
@@ -223,7 +261,7 @@ static int make_mn_tmap(CUtensorMap* m, const void* p, int64_t ld, int R, int C,
 
 template <int BN, int CL>
 static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, int R, int N1,
-                        int N2, cudaStream_t stream) {
+                        int N2, float* db, cudaStream_t stream) {
   using Cfg = WgCfg<BN, CL>;
   constexpr int CS = CL;
   alignas(64) CUtensorMap tmA, tmB, tmC;
@@ -270,15 +308,15 @@ static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, R, N1, N2, splits, per);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, R, N1, N2, splits, per, db);
   if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "gemm_bf16_wgrad_kernel: launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_wgrad_kernel");
 }
 
 }  // namespace tcow
 
-extern "C" int tcow_gemm_bf16_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
-                                    int R, int N1, int N2, void* stream) {
+extern "C" int tcow_gemm_bf16_wgrad_bias(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
+                                         float* db, int R, int N1, int N2, void* stream) {
   using namespace tcow;
   if (!A || !B || !dW) return set_error(TCOW_ERR_ARG, "wgrad: null pointer");
   if (R <= 0 || N1 <= 0 || N2 <= 0) return set_error(TCOW_ERR_ARG, "wgrad: non-positive dimension");
@@ -288,12 +326,17 @@ extern "C" int tcow_gemm_bf16_wgrad(const void* A, int64_t lda, const void* B, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // Clusters of two CTAs (adjacent n1 tiles, B tile TMA-multicast) measured SLOWER than stand-alone CTAs for every
   // weight-gradient shape of the model (qkv 1142 vs 1206, fc2 1129 vs 1199 TFLOP/s: the long row loop keeps the B slab in
-  // L2 anyway, and the cluster couples the two CTAs' stage recycling): off unless TCOW_WGRAD_CLUSTER=2.
+  // L2 anyway, and the cluster couples the two CTAs' stage recycling): off unless TCOW_WGRAD_CLUSTER=2 (never with db).
   static const bool want_cluster = [] { const char* e = getenv("TCOW_WGRAD_CLUSTER"); return e && e[0] == '2'; }();
-  const bool pairs = ((N1 + WG_BM - 1) / WG_BM) % 2 == 0 && want_cluster;
+  const bool pairs = ((N1 + WG_BM - 1) / WG_BM) % 2 == 0 && want_cluster && db == nullptr;
   if (N2 % 256 == 0) {
-    if (pairs) return launch_wgrad<256, 2>(A, lda, B, ldb, dW, ldw, R, N1, N2, s);
-    return launch_wgrad<256, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, s);
+    if (pairs) return launch_wgrad<256, 2>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, s);
+    return launch_wgrad<256, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, s);
   }
-  return launch_wgrad<64, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, s);
+  return launch_wgrad<64, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, s);
+}
+
+extern "C" int tcow_gemm_bf16_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
+                                    int R, int N1, int N2, void* stream) {
+  return tcow_gemm_bf16_wgrad_bias(A, lda, B, ldb, dW, ldw, nullptr, R, N1, N2, stream);
 }

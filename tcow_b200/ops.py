@@ -182,15 +182,20 @@ def gemm_aux(a, w, bias, out, aux, epilogue):
     return out
 
 
-def gemm_wgrad(dy, x, dw):
-    """dw[N1,N2] (fp32) += dy[R,N1]^T @ x[R,N2]  (bf16 operands, contraction over the token rows)."""
+def gemm_wgrad(dy, x, dw, db=None):
+    """dw[N1,N2] (fp32) += dy[R,N1]^T @ x[R,N2]  (bf16 operands, contraction over the token rows); with db (fp32 [N1]) also
+    db += dy.sum(0), the bias gradient, from the same pass over dy."""
     _chk(dy, torch.bfloat16, 'gemm_wgrad.dy'); _chk(x, torch.bfloat16, 'gemm_wgrad.x'); _chk(dw, torch.float32, 'gemm_wgrad.dw')
     R, N1 = dy.shape
     N2 = x.shape[1]
     if x.shape[0] != R or tuple(dw.shape) != (N1, N2):
         raise ValueError(f'gemm_wgrad: shape mismatch dy{tuple(dy.shape)} x{tuple(x.shape)} dw{tuple(dw.shape)}')
-    _lib.call('tcow_gemm_bf16_wgrad', dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
-              dw.stride(0), R, N1, N2, _stream())
+    if db is not None:
+        _chk(db, torch.float32, 'gemm_wgrad.db')
+        if db.numel() != N1 or not db.is_contiguous():
+            raise ValueError('gemm_wgrad: db must be a contiguous fp32 vector of N1 entries')
+    _lib.call('tcow_gemm_bf16_wgrad_bias', dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
+              dw.stride(0), _p(db), R, N1, N2, _stream())
     return dw
 
 

@@ -119,9 +119,10 @@ class SeekerTrainEngine:
         self._launch(kind, ops.gemm, a, w, bias, out, epi, flops=2.0 * M * N * K,
                      nbytes=2.0 * (M * K + N * K) + out.element_size() * M * N * (2 if epi == EPI_F32_ADD else 1))
 
-    def _wgrad(self, kind, dy, x, dw):
+    def _wgrad(self, kind, dy, x, dw, db=None):
+        """dw += dy^T x; with db also db += dy.sum(0) (the layer's bias gradient, from the same pass over dy)."""
         R, N1 = dy.shape
-        self._launch(kind, ops.gemm_wgrad, dy, x, dw, flops=2.0 * R * N1 * x.shape[1],
+        self._launch(kind, ops.gemm_wgrad, dy, x, dw, db, flops=2.0 * R * N1 * x.shape[1],
                      nbytes=2.0 * R * (N1 + x.shape[1]) + 4.0 * dw.numel())
 
     # ------------------------------------------------------------------ weights (repacked every step: they change)
@@ -421,8 +422,7 @@ class SeekerTrainEngine:
                 d_flags = d_flags.to(torch.float32).contiguous()
             L('mask_head_bwd', ops.mask_head_bwd, d_mask, d_flags, dLOW[:M], B, T, Ho, Wo, sv.C, pk.pp, pk.stride, sv.mode,
               max(sv.F, 0), pk.flag_col0, nbytes=4.0 * d_mask.numel())
-            WG('wgrad_head', dLOW[:M], sv.A_f, gv('head_w'))
-            colsum(dLOW[:M], 'head_b')
+            WG('wgrad_head', dLOW[:M], sv.A_f, gv('head_w'), gv('head_b'))
             if sv.norm_embeddings:
                 G('dgrad_head', dLOW[:M], pk.head[2], None, dA[:M], EPI_BF16)
                 ln_bwd(M, sv.xh_f, sv.rs_f, pk.norm[0], 'norm_g', 'norm_b', accumulate=False)
@@ -448,11 +448,9 @@ class SeekerTrainEngine:
                 # ---- MLP (vit.py:216)
                 if dp is not None:
                     Gs = scaled(R, dp['rs_m'], ('m', bi))
-                colsum(Gs, p + 'fc2_b')
-                WG('wgrad_fc2', Gs, s.H, gv(p + 'fc2_w'))
+                WG('wgrad_fc2', Gs, s.H, gv(p + 'fc2_w'), gv(p + 'fc2_b'))
                 L('dgrad_fc2', ops.gemm_aux, Gs, w.fc2[2], None, dZ, s.Z, EPI_BF16_DGELU, flops=2.0 * R * 4 * D * D)
-                colsum(dZ, p + 'fc1_b')
-                WG('wgrad_fc1', dZ, s.A_m, gv(p + 'fc1_w'))
+                WG('wgrad_fc1', dZ, s.A_m, gv(p + 'fc1_w'), gv(p + 'fc1_b'))
                 G('dgrad_fc1', dZ, w.fc1[2], None, dA, EPI_BF16)
                 if dp is not None:
                     ln_bwd(R, s.xh_m, s.rs_m, w.n2[0], p + 'n2_g', p + 'n2_b', next_scale=dp['rs_s_pad'], tag=('s', bi))
@@ -465,9 +463,7 @@ class SeekerTrainEngine:
                     colsum(Gs[:M], p + 's_proj_b')
                     if use_cls:      # cls rows: the bias term carries its own scale (mean of the frame scales, causal==0)
                         gv(p + 's_proj_b').add_((dp['bs_s'][M:R, None] * Gb[M:R].float()).sum(0))
-                else:
-                    colsum(Gs[:Rs], p + 's_proj_b')
-                WG('wgrad_proj', Gs[:Rs], s.O_s, gv(p + 's_proj_w'))
+                WG('wgrad_proj', Gs[:Rs], s.O_s, gv(p + 's_proj_w'), None if dp is not None else gv(p + 's_proj_b'))
                 G('dgrad_proj', Gs[:Rs], w.s_proj[2], None, dO[:Rs], EPI_BF16)
                 dOCLS = None
                 dCLS = torch.empty((ops.spatial_bwd_scratch_floats(B, T, HEADS),), device=device, dtype=torch.float32)
@@ -479,8 +475,7 @@ class SeekerTrainEngine:
                 S = N + (1 if use_cls else 0)
                 L('attn_spatial_bwd', ops.attn_spatial_bwd, s.QKV_s, s.O_s, s.OCLS, dO, dOCLS, s.LSE, dQKV, dCLS, B, N, T,
                   HEADS, use_cls, M, flops=10.0 * B * T * HEADS * S * S * 64, nbytes=16.0 * M * D)
-                colsum(dQKV[:Rs], p + 's_qkv_b')
-                WG('wgrad_qkv', dQKV[:Rs], s.A_s, gv(p + 's_qkv_w'))
+                WG('wgrad_qkv', dQKV[:Rs], s.A_s, gv(p + 's_qkv_w'), gv(p + 's_qkv_b'))
                 G('dgrad_qkv', dQKV[:Rs], w.s_qkv[2], None, dA[:Rs], EPI_BF16)
                 if dp is not None and merged:
                     ln_bwd(Rs, s.xh_s, s.rs_s, w.n1[0], p + 'n1_g', p + 'n1_b', next_scale=dp['rs_t_pad'], tag=('t', bi))
@@ -492,20 +487,16 @@ class SeekerTrainEngine:
                     if dp is not None:
                         Gs = scaled(M, dp['rs_t'], ('t', bi))
                         colsum(Gb[:M], p + 't_out_b2')          # temporal_fc.bias sits outside DropPath
-                    colsum(Gs[:M], p + 't_out_b')
-                    WG('wgrad_proj', Gs[:M], s.O_t, gv(p + 't_out_w'))
+                    WG('wgrad_proj', Gs[:M], s.O_t, gv(p + 't_out_w'), gv(p + 't_out_b'))
                     G('dgrad_proj', Gs[:M], w.t_out[2], None, dO[:M], EPI_BF16)
                 else:
-                    colsum(Gb[:M], p + 't_fc_b')
-                    WG('wgrad_proj', Gb[:M], s.P_t, gv(p + 't_fc_w'))
+                    WG('wgrad_proj', Gb[:M], s.P_t, gv(p + 't_fc_w'), gv(p + 't_fc_b'))
                     G('dgrad_proj', Gb[:M], w.t_fc[2], None, dA[:M], EPI_BF16)      # d(proj output)
-                    colsum(dA[:M], p + 't_proj_b')
-                    WG('wgrad_proj', dA[:M], s.O_t, gv(p + 't_proj_w'))
+                    WG('wgrad_proj', dA[:M], s.O_t, gv(p + 't_proj_w'), gv(p + 't_proj_b'))
                     G('dgrad_proj', dA[:M], w.t_proj[2], None, dO[:M], EPI_BF16)
                 L('attn_temporal_bwd', ops.attn_temporal_bwd, s.QKV_t, s.O_t, dO, dQKV, B * N, T, HEADS, causal_diag,
                   flops=10.0 * B * N * HEADS * T * T * 64, nbytes=16.0 * M * D)
-                colsum(dQKV[:M], p + 't_qkv_b')
-                WG('wgrad_qkv', dQKV[:M], s.A_t, gv(p + 't_qkv_w'))
+                WG('wgrad_qkv', dQKV[:M], s.A_t, gv(p + 't_qkv_w'), gv(p + 't_qkv_b'))
                 G('dgrad_qkv', dQKV[:M], w.t_qkv[2], None, dA[:M], EPI_BF16)
                 dp_prev = sv.blocks[bi - 1].dp if bi > 0 else None
                 if dp_prev is not None:   # the MLP branch of block bi-1 is next: its scale for the patch rows here, cls rows apart

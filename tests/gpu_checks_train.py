@@ -21,7 +21,7 @@ def _relerr(got, ref):
     return ((got - ref).norm() / ref.norm().clamp_min(1e-20)).item()
 
 
-def check_wgrad(R, N1, N2, accumulate=False, pad=0):
+def check_wgrad(R, N1, N2, accumulate=False, pad=0, bias=False):
     d = _dev()
     g = torch.Generator(device=d).manual_seed(11)
     dy_full = (torch.randn(R, N1 + pad, device=d, generator=g) * 0.3).to(torch.bfloat16)
@@ -29,12 +29,20 @@ def check_wgrad(R, N1, N2, accumulate=False, pad=0):
     dy, x = dy_full[:, :N1], x_full[:, :N2]          # pitch != width when pad > 0
     base = torch.randn(N1, N2, device=d, generator=g) if accumulate else torch.zeros(N1, N2, device=d)
     dw = base.clone()
-    ops.gemm_wgrad(dy, x, dw)
+    db0 = torch.randn(N1, device=d, generator=g) if accumulate else torch.zeros(N1, device=d)
+    db = db0.clone() if bias else None
+    ops.gemm_wgrad(dy, x, dw, db)
     torch.cuda.synchronize()
     ref = base + dy.float().t() @ x.float()
     err = (dw - ref).abs().max().item()
     tol = 2e-5 * ref.abs().max().item() + 1e-4 * (R / 1000) ** 0.5
-    return err, tol, f'wgrad R={R} N1={N1} N2={N2} acc={accumulate} pad={pad} (rel {_relerr(dw, ref):.2e})'
+    extra = ''
+    if bias:      # bias gradient from the same pass: db += dy.sum(0)
+        ref_b = db0 + dy.float().sum(0)
+        err_b = (db - ref_b).abs().max().item()
+        extra = f' db err {err_b:.2e}'
+        err = max(err, err_b * tol / (1e-5 * ref_b.abs().max().item() + 2e-4 * (R / 1000) ** 0.5))
+    return err, tol, f'wgrad R={R} N1={N1} N2={N2} acc={accumulate} pad={pad} (rel {_relerr(dw, ref):.2e}){extra}'
 
 
 def check_gemm_gelu_aux(M, N, K):
@@ -297,6 +305,12 @@ TRAIN_CHECKS = [
     ('wgrad_proj', lambda: check_wgrad(54000, 768, 768)),
     ('wgrad_patch', lambda: check_wgrad(54000, 768, 1024)),
     ('wgrad_one_row', lambda: check_wgrad(1, 64, 64)),
+    ('wgrad_bias_small', lambda: check_wgrad(300, 128, 256, bias=True)),
+    ('wgrad_bias_ragged', lambda: check_wgrad(1001, 192, 512, accumulate=True, bias=True)),
+    ('wgrad_bias_n1_64', lambda: check_wgrad(5000, 64, 768, bias=True)),
+    ('wgrad_bias_bn64', lambda: check_wgrad(777, 256, 192, bias=True)),
+    ('wgrad_bias_qkv', lambda: check_wgrad(54006, 2304, 768, bias=True)),
+    ('wgrad_bias_fc2', lambda: check_wgrad(54006, 768, 3072, accumulate=True, bias=True)),
     ('gemm_gelu_aux', lambda: check_gemm_gelu_aux(9001, 3072, 768)),
     ('gemm_gelu_aux_small', lambda: check_gemm_gelu_aux(100, 128, 64)),
     ('gemm_dgelu', lambda: check_gemm_dgelu(9001, 3072, 768)),

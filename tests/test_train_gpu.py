@@ -113,7 +113,10 @@ def test_training_forward_equals_inference_forward(logger):
     _, _, mask_train = our_grads(net, rgb, q, tm, tf)
     with torch.no_grad():
         mask_inf, _ = net(rgb.to(DEV), q.to(DEV))
-    assert (mask_train - mask_inf).abs().max().item() <= 2e-3
+    # same plan, but the inference path embeds the patches with the one-kernel form (accumulate, then add the embeddings)
+    # and the training path with gather + embed_init + reduce-add GEMM (embeddings first): different fp32 rounding in the
+    # first layer, amplified by 12 bf16 blocks to ~3e-3 — two equally valid bf16 evaluations of the same function
+    assert (mask_train - mask_inf).abs().max().item() <= 5e-3
 
 
 def test_query_loop_then_one_backward_and_accumulation(logger):
