@@ -238,6 +238,13 @@ int tcow_gemm_bf16_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb,
  * tcow_colsum_bf16 pass).  db == NULL: exactly tcow_gemm_bf16_wgrad. */
 int tcow_gemm_bf16_wgrad_bias(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, float* db,
                               int R, int N1, int N2, void* stream);
+/* The same with ticket scheduling: sched = two ints of device memory, zero before the first launch (the kernel leaves them
+ * zero again).  The row splits become finer (about three units per SM) and every CTA takes its next unit from an atomic
+ * counter, so SMs that are late or shared with a concurrent kernel — NCCL's all-reduce of the previous gradient bucket
+ * during the data-parallel backward (train.py:222-223 is where the reference parallelises) — take fewer units instead of
+ * stretching the kernel.  sched == NULL: static striping. */
+int tcow_gemm_bf16_wgrad_sched(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, float* db,
+                               int* sched, int R, int N1, int N2, void* stream);
 
 /* Floats of scratch the reductions below need (LayerNorm-backward / column-sum / time-embedding partial sums). */
 int64_t tcow_train_workspace_floats(int max_cols);

@@ -65,6 +65,8 @@ SIGNATURES = {
     'tcow_gemm_bf16_wgrad': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     'tcow_gemm_bf16_wgrad_bias': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int,
                                   c_void_p],
+    'tcow_gemm_bf16_wgrad_sched': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_void_p],
     'tcow_train_workspace_floats': [c_int],
     'tcow_layernorm_bf16_train': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                   c_void_p],

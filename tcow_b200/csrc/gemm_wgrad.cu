@@ -31,7 +31,7 @@ struct WgCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_WARP_BYTES = 32 * 128;
   static constexpr int OUT_BYTES = 4 * 2 * OUT_WARP_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_MAX = 232448;
   static constexpr int STAGES_FIT = (SMEM_MAX - 1024 - BAR_BYTES - OUT_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -51,7 +51,7 @@ template <int BN, int CL>
 __global__ void __launch_bounds__(WgCfg<BN, CL>::THREADS, 1)
 gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, int R, int N1, int N2, int splits, int kb_per_split,
-                       float* __restrict__ db) {
+                       float* __restrict__ db, int* __restrict__ sched) {
   using Cfg = WgCfg<BN, CL>;
   constexpr int CS = CL;
   constexpr int STAGES = Cfg::STAGES;
@@ -66,6 +66,14 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_wg + (tmem_slot - raw));
+  // Unit ring: the producer warp decides which unit comes next — statically striped, or (sched != nullptr) by an atomic
+  // ticket — and publishes it to the MMA, epilogue and bias warps.  With tickets and several units per SM, SMs that are
+  // late or busy with another kernel (NCCL's all-reduce during the data-parallel backward) simply take fewer units
+  // instead of leaving a tail: wgrad_fc2 ran 68 % longer on 8 GPUs than on one with static striping.
+  constexpr int UR = 4;
+  auto ufull_bar = [&](int i) { return bars + 8u * (2 * STAGES + 5 + i); };
+  auto uempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 5 + UR + i); };
+  volatile int* s_units = reinterpret_cast<volatile int*>(smem_wg + (bars + 8u * (2 * STAGES + 5 + 2 * UR) - raw));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,6 +109,10 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
     }
+    for (int i = 0; i < UR; ++i) {
+      mbar_init(ufull_bar(i), 1);
+      mbar_init(uempty_bar(i), 1 + 4 + (db ? 2 : 0));   // MMA warp, four epilogue warps, two bias warps
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -112,11 +124,31 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (CS > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast can land on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // k-th unit of this CTA as published by the producer warp (-1: no more work)
+  auto next_unit = [&](uint32_t k) {
+    const int slot = k % UR;
+    mbar_wait(ufull_bar(slot), (k / UR) & 1);
+    const int u = s_units[slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(uempty_bar(slot));
+    return u;
+  };
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
+    // ------------------------------------------------ unit scheduler + TMA producer
     uint32_t it = 0;
-    for (int u = unit0; u < units; u += unit_step) {
+    for (uint32_t k = 0;; ++k) {
+      const int slot = k % UR;
+      mbar_wait(uempty_bar(slot), ((k / UR) & 1) ^ 1);
+      int u = 0;
+      if (lane == 0) {
+        u = sched ? atomicAdd(sched, 1) : unit0 + static_cast<int>(k) * unit_step;
+        if (u >= units) u = -1;
+        s_units[slot] = u;
+        mbar_arrive(ufull_bar(slot));
+      }
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u < 0) break;
       int m_blk, n_blk, kb0, kb1;
       unit_at(u, m_blk, n_blk, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -141,7 +173,9 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = wg_idesc(WG_BM, BN);
     uint32_t it = 0, t = 0;
-    for (int u = unit0; u < units; u += unit_step, ++t) {
+    for (;; ++t) {
+      const int u = next_unit(t);
+      if (u < 0) break;
       int m_blk, n_blk, kb0, kb1;
       unit_at(u, m_blk, n_blk, kb0, kb1);
       const int acc = t & 1;
@@ -175,7 +209,9 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t col_off = (tcol >> 5) * (WG_BK * 128) + ((tcol & 3) << 2);   // 64-column block, word inside the 16-B chunk
     const uint32_t chunk = (tcol & 31) >> 2;
     uint32_t it = 0;
-    for (int u = unit0; u < units; u += unit_step) {
+    for (uint32_t k = 0;; ++k) {
+      const int u = next_unit(k);
+      if (u < 0) break;
       int m_blk, n_blk, kb0, kb1;
       unit_at(u, m_blk, n_blk, kb0, kb1);
       float s0 = 0.f, s1 = 0.f;
@@ -208,7 +244,9 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t srow = lane * 128;
     const uint32_t sw = lane & 7;
     uint32_t t = 0, cc = 0;
-    for (int u = unit0; u < units; u += unit_step, ++t) {
+    for (;; ++t) {
+      const int u = next_unit(t);
+      if (u < 0) break;
       int m_blk, n_blk, kb0, kb1;
       unit_at(u, m_blk, n_blk, kb0, kb1);
       const int acc = t & 1;
@@ -248,6 +286,14 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   __syncthreads();
   if (CS > 1) cluster_sync_all();  // no CTA exits while its peer may still multicast into it or signal its barriers
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (sched && threadIdx.x == 0) {   // the last CTA to leave puts the ticket counters back to zero for the next launch
+    __threadfence();
+    if (atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // [R, C] row-major bf16 seen as (64 columns, R rows, C/64 column blocks): one box lands in smem as
@@ -261,7 +307,7 @@ static int make_mn_tmap(CUtensorMap* m, const void* p, int64_t ld, int R, int C,
 
 template <int BN, int CL>
 static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, int R, int N1,
-                        int N2, float* db, cudaStream_t stream) {
+                        int N2, float* db, int* sched, cudaStream_t stream) {
   using Cfg = WgCfg<BN, CL>;
   constexpr int CS = CL;
   alignas(64) CUtensorMap tmA, tmB, tmC;
@@ -292,6 +338,11 @@ static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, 
       best = s;
     }
   }
+  if (sched != nullptr) {   // ticket scheduling wants several units per SM (finer row splits), each still >= 8 k-blocks
+    const int want = (3 * sms + tiles - 1) / tiles;
+    const int cap = num_kb / 8 > 1 ? num_kb / 8 : 1;
+    if (want > best) best = want < cap ? want : cap;
+  }
   const int per = (num_kb + best - 1) / best;
   const int splits = (num_kb + per - 1) / per;  // no empty split
   const int units = tiles * splits;
@@ -308,15 +359,15 @@ static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, R, N1, N2, splits, per, db);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, R, N1, N2, splits, per, db, sched);
   if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "gemm_bf16_wgrad_kernel: launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_wgrad_kernel");
 }
 
 }  // namespace tcow
 
-extern "C" int tcow_gemm_bf16_wgrad_bias(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
-                                         float* db, int R, int N1, int N2, void* stream) {
+extern "C" int tcow_gemm_bf16_wgrad_sched(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
+                                          float* db, int* sched, int R, int N1, int N2, void* stream) {
   using namespace tcow;
   if (!A || !B || !dW) return set_error(TCOW_ERR_ARG, "wgrad: null pointer");
   if (R <= 0 || N1 <= 0 || N2 <= 0) return set_error(TCOW_ERR_ARG, "wgrad: non-positive dimension");
@@ -328,15 +379,20 @@ extern "C" int tcow_gemm_bf16_wgrad_bias(const void* A, int64_t lda, const void*
   // weight-gradient shape of the model (qkv 1142 vs 1206, fc2 1129 vs 1199 TFLOP/s: the long row loop keeps the B slab in
   // L2 anyway, and the cluster couples the two CTAs' stage recycling): off unless TCOW_WGRAD_CLUSTER=2 (never with db).
   static const bool want_cluster = [] { const char* e = getenv("TCOW_WGRAD_CLUSTER"); return e && e[0] == '2'; }();
-  const bool pairs = ((N1 + WG_BM - 1) / WG_BM) % 2 == 0 && want_cluster && db == nullptr;
+  const bool pairs = ((N1 + WG_BM - 1) / WG_BM) % 2 == 0 && want_cluster && db == nullptr && sched == nullptr;
   if (N2 % 256 == 0) {
-    if (pairs) return launch_wgrad<256, 2>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, s);
-    return launch_wgrad<256, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, s);
+    if (pairs) return launch_wgrad<256, 2>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, sched, s);
+    return launch_wgrad<256, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, sched, s);
   }
-  return launch_wgrad<64, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, s);
+  return launch_wgrad<64, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, sched, s);
+}
+
+extern "C" int tcow_gemm_bf16_wgrad_bias(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
+                                         float* db, int R, int N1, int N2, void* stream) {
+  return tcow_gemm_bf16_wgrad_sched(A, lda, B, ldb, dW, ldw, db, nullptr, R, N1, N2, stream);
 }
 
 extern "C" int tcow_gemm_bf16_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
                                     int R, int N1, int N2, void* stream) {
-  return tcow_gemm_bf16_wgrad_bias(A, lda, B, ldb, dW, ldw, nullptr, R, N1, N2, stream);
+  return tcow_gemm_bf16_wgrad_sched(A, lda, B, ldb, dW, ldw, nullptr, nullptr, R, N1, N2, stream);
 }

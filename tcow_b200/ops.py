@@ -182,9 +182,10 @@ def gemm_aux(a, w, bias, out, aux, epilogue):
     return out
 
 
-def gemm_wgrad(dy, x, dw, db=None):
+def gemm_wgrad(dy, x, dw, db=None, sched=None):
     """dw[N1,N2] (fp32) += dy[R,N1]^T @ x[R,N2]  (bf16 operands, contraction over the token rows); with db (fp32 [N1]) also
-    db += dy.sum(0), the bias gradient, from the same pass over dy."""
+    db += dy.sum(0), the bias gradient, from the same pass over dy; with sched (int32[2], zero-initialised once) the units are
+    handed out by an atomic ticket instead of static striping (robust against SMs shared with a concurrent kernel)."""
     _chk(dy, torch.bfloat16, 'gemm_wgrad.dy'); _chk(x, torch.bfloat16, 'gemm_wgrad.x'); _chk(dw, torch.float32, 'gemm_wgrad.dw')
     R, N1 = dy.shape
     N2 = x.shape[1]
@@ -194,8 +195,10 @@ def gemm_wgrad(dy, x, dw, db=None):
         _chk(db, torch.float32, 'gemm_wgrad.db')
         if db.numel() != N1 or not db.is_contiguous():
             raise ValueError('gemm_wgrad: db must be a contiguous fp32 vector of N1 entries')
-    _lib.call('tcow_gemm_bf16_wgrad_bias', dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
-              dw.stride(0), _p(db), R, N1, N2, _stream())
+    if sched is not None and (sched.dtype != torch.int32 or sched.numel() < 2 or not sched.is_cuda):
+        raise ValueError('gemm_wgrad: sched must be a CUDA int32 tensor of 2 entries')
+    _lib.call('tcow_gemm_bf16_wgrad_sched', dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
+              dw.stride(0), _p(db), _p(sched), R, N1, N2, _stream())
     return dw
 
 

@@ -20,6 +20,8 @@ gradients are mapped back onto the reference's 251 parameters by small fp32 weig
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -96,6 +98,7 @@ class SeekerTrainEngine:
         self.launches = 0
         self.profile = None
         self.grad_sync = None        # optional ddp.GradSync: all-reduces finished ranges of the flat gradient buffer
+        self._tickets = {}           # device index -> int32[2] ticket counters of the weight-gradient GEMM scheduler
         # tests inject fixed stochastic-depth keep masks here: list (one per block) of None or
         # dict(t=[B*N], s=[B*T], m=[B]) 0/1 tensors; None = draw them (vit_utils.py:139-164)
         self.drop_path_override = None
@@ -122,8 +125,20 @@ class SeekerTrainEngine:
     def _wgrad(self, kind, dy, x, dw, db=None):
         """dw += dy^T x; with db also db += dy.sum(0) (the layer's bias gradient, from the same pass over dy)."""
         R, N1 = dy.shape
-        self._launch(kind, ops.gemm_wgrad, dy, x, dw, db, flops=2.0 * R * N1 * x.shape[1],
+        self._launch(kind, ops.gemm_wgrad, dy, x, dw, db, self._wgrad_tickets(dy.device), flops=2.0 * R * N1 * x.shape[1],
                      nbytes=2.0 * R * (N1 + x.shape[1]) + 4.0 * dw.numel())
+
+    def _wgrad_tickets(self, device):
+        """Ticket counters of the weight-gradient GEMM's dynamic unit scheduler (ops.gemm_wgrad `sched`).  It matters when a
+        gradient exchange runs beside the backward (ddp.attach): NCCL's all-reduce kernels then share the SMs, and static
+        striping leaves a tail behind the SMs they occupy.  On one GPU it measured neutral (60.4 vs 59.9 ms per step), so it
+        is simply always on; TCOW_WGRAD_SCHED=0 goes back to static striping."""
+        if os.environ.get('TCOW_WGRAD_SCHED', '1') == '0':
+            return None
+        t = self._tickets.get(device.index)
+        if t is None:
+            t = self._tickets[device.index] = torch.zeros(2, device=device, dtype=torch.int32)
+        return t
 
     # ------------------------------------------------------------------ weights (repacked every step: they change)
     def _pack(self, mod, device):

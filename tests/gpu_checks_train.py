@@ -21,8 +21,9 @@ def _relerr(got, ref):
     return ((got - ref).norm() / ref.norm().clamp_min(1e-20)).item()
 
 
-def check_wgrad(R, N1, N2, accumulate=False, pad=0, bias=False):
+def check_wgrad(R, N1, N2, accumulate=False, pad=0, bias=False, tickets=False):
     d = _dev()
+    sched = torch.zeros(2, device=d, dtype=torch.int32) if tickets else None
     g = torch.Generator(device=d).manual_seed(11)
     dy_full = (torch.randn(R, N1 + pad, device=d, generator=g) * 0.3).to(torch.bfloat16)
     x_full = (torch.randn(R, N2 + pad, device=d, generator=g) * 0.7).to(torch.bfloat16)
@@ -31,7 +32,15 @@ def check_wgrad(R, N1, N2, accumulate=False, pad=0, bias=False):
     dw = base.clone()
     db0 = torch.randn(N1, device=d, generator=g) if accumulate else torch.zeros(N1, device=d)
     db = db0.clone() if bias else None
-    ops.gemm_wgrad(dy, x, dw, db)
+    ops.gemm_wgrad(dy, x, dw, db, sched)
+    if tickets:      # the counters come back to zero: a second launch on the same counters must work
+        ops.gemm_wgrad(dy, x, dw, db, sched)
+        torch.cuda.synchronize()
+        if int(sched.abs().sum()) != 0:
+            return float('inf'), 0.0, 'wgrad ticket counters not reset'
+        dw.sub_(base).mul_(0.5).add_(base)
+        if db is not None:
+            db.sub_(db0).mul_(0.5).add_(db0)
     torch.cuda.synchronize()
     ref = base + dy.float().t() @ x.float()
     err = (dw - ref).abs().max().item()
@@ -311,6 +320,11 @@ TRAIN_CHECKS = [
     ('wgrad_bias_bn64', lambda: check_wgrad(777, 256, 192, bias=True)),
     ('wgrad_bias_qkv', lambda: check_wgrad(54006, 2304, 768, bias=True)),
     ('wgrad_bias_fc2', lambda: check_wgrad(54006, 768, 3072, accumulate=True, bias=True)),
+    ('wgrad_tickets_small', lambda: check_wgrad(300, 128, 256, bias=True, tickets=True)),
+    ('wgrad_tickets_bn64', lambda: check_wgrad(777, 256, 192, tickets=True)),
+    ('wgrad_tickets_qkv', lambda: check_wgrad(54006, 2304, 768, bias=True, tickets=True)),
+    ('wgrad_tickets_fc2', lambda: check_wgrad(54006, 768, 3072, accumulate=True, bias=True, tickets=True)),
+    ('wgrad_tickets_proj', lambda: check_wgrad(54000, 768, 768, tickets=True)),
     ('gemm_gelu_aux', lambda: check_gemm_gelu_aux(9001, 3072, 768)),
     ('gemm_gelu_aux_small', lambda: check_gemm_gelu_aux(100, 128, 64)),
     ('gemm_dgelu', lambda: check_gemm_dgelu(9001, 3072, 768)),

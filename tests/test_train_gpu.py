@@ -181,7 +181,7 @@ def test_stochastic_depth_draws(logger):
     assert torch.equal(c, d)
     with torch.no_grad():
         e, _ = net(rgb.to(DEV), q.to(DEV))
-    assert (c - e).abs().max().item() <= 2e-3
+    assert (c - e).abs().max().item() <= 5e-3      # training plan vs inference plan: see test_training_forward_equals_inference_forward
     scales = net.seeker.train_engine()._drop_path_scales(net.seeker.train(), 12, 2, 6, 4, 48, 50, 50, True, 1, torch.device(DEV))
     assert scales[0] is None and all(s is not None for s in scales[1:])
     last = scales[-1]['rs_t']
