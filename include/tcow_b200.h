@@ -76,14 +76,6 @@ int tcow_layernorm_bf16(const float* x, const float* gamma, const float* beta, v
 int tcow_attn_temporal(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int num_seq, int T,
                        int heads, int causal_diag, void* stream);
 
-/* Fused qkv projection + temporal attention (vit.py:81-109 as called at :172): out[rows, heads*64] (bf16) =
- * attn_temporal(A W^T + b) without materialising the qkv tensor.  A is [num_seq*T, K] bf16; Wperm [heads*192, K]
- * bf16 and bias_perm [heads*192] fp32 are the qkv Linear's rows regrouped head-major: row h*192 + p*64 + d is
- * original row p*(heads*64) + h*64 + d (p = 0,1,2 for q,k,v).  Same mask convention as tcow_attn_temporal. */
-int tcow_qkv_temporal_attn(const void* A, int64_t lda, const void* Wperm, int64_t ldw, const float* bias_perm,
-                           void* out, int64_t ld_out, int num_seq, int T, int heads, int K, int causal_diag,
-                           void* stream);
-
 /* Spatial attention (vit.py:186 on the tokens assembled at :179-185): for each clip b, frame t, head:
  * full softmax attention over [cls(b) ; patches n=0..N-1 of frame t] (use_cls=1) or the patches only
  * (use_cls=0, causal_attention >= 2 or -1, vit.py:202-208).  Patch rows are read/written in place in the

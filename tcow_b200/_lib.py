@@ -25,8 +25,6 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p],
     'tcow_layernorm_bf16': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     'tcow_attn_temporal': [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p],
-    'tcow_qkv_temporal_attn': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
-                               c_int, c_int, c_void_p],
     'tcow_attn_spatial': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                           c_int64, c_void_p],
     'tcow_cls_merge': [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_int, c_void_p],

@@ -16,7 +16,6 @@ from __future__ import annotations
 
 import os
 
-import numpy as np
 import torch
 
 from . import seeker as seeker_mod
@@ -39,43 +38,38 @@ def build_seeker(logger, seeker_args, state_dict=None, device=None):
     return net
 
 
+def resolve_checkpoint_file(path, epoch=-1):
+    """A checkpoint directory holds `checkpoint.pth` (latest) and `model_<epoch>.pth` snapshots (train.py:269-304)."""
+    if not os.path.exists(path):
+        raise AssertionError(f'checkpoint path does not exist: {path}')       # the reference asserts (inference.py:28)
+    if not os.path.isdir(path):
+        return path
+    return os.path.join(path, 'checkpoint.pth' if epoch < 0 else f'model_{epoch}.pth')
+
+
 def load_networks(checkpoint_path, device, logger, epoch=-1):
-    '''
-    Drop-in for eval/inference.py:19-57.
-    :param checkpoint_path (str): Path to model checkpoint folder or file.
-    :param epoch (int): If >= 0, desired checkpoint epoch to load.
-    :return (networks, train_args, dset_args, model_args, epoch).
-    '''
-    print_fn = logger.info if logger is not None else print
-    assert os.path.exists(checkpoint_path)
-    if os.path.isdir(checkpoint_path):
-        model_fn = f'model_{epoch}.pth' if epoch >= 0 else 'checkpoint.pth'
-        checkpoint_path = os.path.join(checkpoint_path, model_fn)
-    print_fn('Loading weights from: ' + checkpoint_path)
-    checkpoint = torch.load(checkpoint_path, map_location='cpu', weights_only=False)
-    train_args = checkpoint['train_args']
-    train_dset_args = checkpoint['dset_args']
-    seeker_args = checkpoint['seeker_args']
-    model_args = {'seeker': seeker_args}
-    seeker_net = build_seeker(logger, seeker_args, checkpoint['net_seeker'], device)
-    networks = {'seeker': seeker_net}
-    epoch = checkpoint['epoch']
-    print_fn('=> Loaded epoch (1-based): ' + str(epoch + 1))
-    return (networks, train_args, train_dset_args, model_args, epoch)
+    """Same call and same 5-tuple as eval/inference.py:19-57 — `(networks, train_args, dset_args, model_args, epoch)` —
+    with the B200 Seeker in `networks['seeker']`.  `epoch >= 0` picks that snapshot of a checkpoint directory."""
+    say = print if logger is None else logger.info
+    file = resolve_checkpoint_file(checkpoint_path, epoch)
+    say(f'Loading weights from: {file}')
+    ckpt = torch.load(file, map_location='cpu', weights_only=False)        # pickled argparse.Namespace inside
+    model_args = {'seeker': ckpt['seeker_args']}
+    networks = {'seeker': build_seeker(logger, model_args['seeker'], ckpt['net_seeker'], device)}
+    say(f"=> Loaded epoch (1-based): {ckpt['epoch'] + 1}")
+    return networks, ckpt['train_args'], ckpt['dset_args'], model_args, ckpt['epoch']
 
 
 def save_model_checkpoint(checkpoint_dir, epoch, train_args, dset_args, seeker_args, networks, optimizers=None,
                           lr_schedulers=None):
-    """Writes what train.py:269-296 writes (checkpoint.pth + checkpoint_epoch.txt), so the reference can read it back."""
+    """Writes the layout the reference reads back (train.py:269-296): `checkpoint.pth` with the argument records, one
+    `net_<name>` / `optim_<name>` / `lr_sched_<name>` state dict per entry, plus `checkpoint_epoch.txt`."""
     os.makedirs(checkpoint_dir, exist_ok=True)
-    checkpoint = {'epoch': epoch, 'train_args': train_args, 'dset_args': dset_args, 'seeker_args': seeker_args}
-    for (k, v) in networks.items():
-        checkpoint['net_' + k] = v.state_dict()
-    for (k, v) in (optimizers or {}).items():
-        checkpoint['optim_' + k] = v.state_dict()
-    for (k, v) in (lr_schedulers or {}).items():
-        checkpoint['lr_sched_' + k] = v.state_dict()
+    record = dict(epoch=epoch, train_args=train_args, dset_args=dset_args, seeker_args=seeker_args)
+    for prefix, group in (('net_', networks), ('optim_', optimizers or {}), ('lr_sched_', lr_schedulers or {})):
+        record.update({prefix + name: obj.state_dict() for name, obj in group.items()})
     path = os.path.join(checkpoint_dir, 'checkpoint.pth')
-    torch.save(checkpoint, path)
-    np.savetxt(os.path.join(checkpoint_dir, 'checkpoint_epoch.txt'), np.array([epoch], dtype=np.int32), fmt='%d')
+    torch.save(record, path)
+    with open(os.path.join(checkpoint_dir, 'checkpoint_epoch.txt'), 'w') as f:
+        f.write(f'{int(epoch)}\n')
     return path

@@ -4,8 +4,8 @@
 // With P = softmax(Q K^T * hd^-0.5 + mask), O = P V and the upstream gradient dO:
 //   D_i = sum_d dO[i,d] O[i,d]          dP = dO V^T           dS = P o (dP - D) * hd^-0.5
 //   dQ = dS K                           dK = dS^T Q           dV = P^T dO
-// P is recomputed from the saved log-sum-exp (spatial: written by the tcgen05 forward; temporal: recomputed here,
-// the sequences are 30 long).  Each 16-row tile of queries (dQ) and of keys (dK, dV) is owned by one warp, which
+// This file holds the TEMPORAL operator (30-long sequences, recomputes its own log-sum-exp) and the entry point of the
+// spatial one, whose kernels are tcgen05/TMEM (attn_spatial_bwd_tc.cu, P recomputed from the forward's saved log-sum-exp).  Each 16-row tile of queries (dQ) and of keys (dK, dV) is owned by one warp, which
 // walks the other dimension in 16-wide steps with mma.sync m16n8k16 (bf16 in, fp32 accumulate) out of XOR-swizzled
 // shared memory; the key-owner pass recomputes S^T = K Q^T so that P^T and dS^T come out of the tensor cores already
 // in A-fragment layout — no transposes, no atomics, deterministic.  Gradients are staged per warp and written as
@@ -322,137 +322,6 @@ __global__ void __launch_bounds__(128) attn_temporal_bwd_kernel(const __nv_bfloa
   }
 }
 
-// ============================================================================================ spatial
-// One CTA per (clip b, frame t, head): the whole S x 64 problem (S = N + use_cls <= 304) lives in shared memory.
-// Token i < N is patch i (canonical row (b*N+i)*T+t); token N is the cls token (row cls_row0+b of qkv; its dO comes
-// from d_out_cls[b,t] and its O from out_cls[b,t], fp32).  The cls token's dq/dk/dv of this frame go to
-// d_cls[b,t,{q,k,v},:] (fp32); tcow_attn_spatial_bwd sums them over the frames into row cls_row0+b of d_qkv.
-constexpr int SPB_ROWS = 304;
-constexpr int SPB_TILE = SPB_ROWS * ROW_BYTES;
-constexpr int SPB_WARPS = 10;
-constexpr int SPB_SMEM = 4 * SPB_TILE + SPB_WARPS * 16 * ROW_BYTES + 2 * SPB_ROWS * 4 + 1024;
-
-__global__ void __launch_bounds__(SPB_WARPS * 32, 1)
-attn_spatial_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv, const __nv_bfloat16* __restrict__ out,
-                        int64_t ld_out, const float* __restrict__ out_cls, const __nv_bfloat16* __restrict__ d_out,
-                        int64_t ld_do, const float* __restrict__ d_out_cls, const float* __restrict__ lse,
-                        __nv_bfloat16* __restrict__ d_qkv, int64_t ld_dqkv, float* __restrict__ d_cls, int B, int N,
-                        int T, int heads, int use_cls, int64_t cls_row0, float scale_log2, float scale) {
-  extern __shared__ uint8_t smem_sb[];
-  const uint32_t raw = smem_u32(smem_sb);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = sQ + SPB_TILE, sV = sK + SPB_TILE, sdO = sV + SPB_TILE;
-  const uint32_t sStage = sdO + SPB_TILE;
-  float* s_lse = reinterpret_cast<float*>(smem_sb + (sStage + SPB_WARPS * 16 * ROW_BYTES - raw));
-  float* s_D = s_lse + SPB_ROWS;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = N + use_cls;
-  const int item = blockIdx.x;  // (b*T + t)*heads + h
-  const int h = item % heads, t = (item / heads) % T, b = item / (heads * T);
-  const int D = heads * HD;
-
-  auto tok_row = [&](int i) -> int64_t { return (static_cast<int64_t>(b) * N + i) * T + t; };
-  // ---- gather q, k, v, dO (patch rows by cp.async; cls row / padding rows by plain stores)
-  for (int idx = threadIdx.x; idx < SPB_ROWS * 8; idx += blockDim.x) {
-    const int row = idx >> 3, chunk = idx & 7;
-    if (row < N) {
-      const __nv_bfloat16* src = qkv + tok_row(row) * ld_qkv + h * HD + chunk * 8;
-      cp_async_16(sw_addr(sQ, row, chunk), src);
-      cp_async_16(sw_addr(sK, row, chunk), src + D);
-      cp_async_16(sw_addr(sV, row, chunk), src + 2 * D);
-      cp_async_16(sw_addr(sdO, row, chunk), d_out + tok_row(row) * ld_do + h * HD + chunk * 8);
-    } else if (row == N && use_cls) {
-      const __nv_bfloat16* src = qkv + (cls_row0 + b) * ld_qkv + h * HD + chunk * 8;
-      cp_async_16(sw_addr(sQ, row, chunk), src);
-      cp_async_16(sw_addr(sK, row, chunk), src + D);
-      cp_async_16(sw_addr(sV, row, chunk), src + 2 * D);
-      const float4* dc = reinterpret_cast<const float4*>(d_out_cls + (static_cast<int64_t>(b) * T + t) * D + h * HD + chunk * 8);
-      const float4 x0 = __ldg(dc), x1 = __ldg(dc + 1);
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sw_addr(sdO, row, chunk)), "r"(pack_bf16(x0.x, x0.y)),
-                   "r"(pack_bf16(x0.z, x0.w)), "r"(pack_bf16(x1.x, x1.y)), "r"(pack_bf16(x1.z, x1.w))
-                   : "memory");
-    } else {
-#pragma unroll
-      for (int w = 0; w < 4; ++w)
-        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sw_addr(sQ + w * SPB_TILE, row, chunk)), "r"(0) : "memory");
-    }
-  }
-  cp_async_commit();
-  for (int i = threadIdx.x; i < SPB_ROWS; i += blockDim.x)
-    s_lse[i] = i < S ? __ldg(lse + static_cast<int64_t>(item) * SPB_ROWS + i) : 0.f;
-  cp_async_wait<0>();
-  __syncthreads();
-  // ---- D_i = dO_i . O_i (O from global: bf16 rows, fp32 for the cls token); 8 lanes per row
-  for (int r0 = warp * 4; r0 < SPB_ROWS; r0 += SPB_WARPS * 4) {
-    const int row = r0 + (lane >> 3), chunk = lane & 7;
-    float s = 0.f;
-    if (row < N) {
-      const uint4 o = __ldg(reinterpret_cast<const uint4*>(out + tok_row(row) * ld_out + h * HD + chunk * 8));
-      s = dot8(lds128(sw_addr(sdO, row, chunk)), o);
-    } else if (row == N && use_cls) {
-      const float4* oc = reinterpret_cast<const float4*>(out_cls + (static_cast<int64_t>(b) * T + t) * D + h * HD + chunk * 8);
-      const float4 o0 = __ldg(oc), o1 = __ldg(oc + 1);
-      const uint4 d = lds128(sw_addr(sdO, row, chunk));
-      s = bfl(d.x) * o0.x + bfh(d.x) * o0.y + bfl(d.y) * o0.z + bfh(d.y) * o0.w + bfl(d.z) * o1.x + bfh(d.z) * o1.y +
-          bfl(d.w) * o1.z + bfh(d.w) * o1.w;
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (chunk == 0 && row < SPB_ROWS) s_D[row] = s;
-  }
-  __syncthreads();
-
-  const uint32_t my_stage = sStage + warp * 16 * ROW_BYTES;
-  // rows [r0, r0+16) of the staged bf16 tile -> column block `which` (0 q, 1 k, 2 v) of d_qkv; cls row -> d_cls (fp32)
-  auto flush = [&](int r0, int which, const float (&tile)[8][4]) {
-    stage_tile(my_stage, tile);
-    __syncwarp();
-    for (int idx = lane; idx < 16 * 8; idx += 32) {
-      const int row = idx >> 3, chunk = idx & 7;
-      if (r0 + row < N)
-        *reinterpret_cast<uint4*>(d_qkv + tok_row(r0 + row) * ld_dqkv + which * D + h * HD + chunk * 8) =
-            lds128(sw_addr(my_stage, row, chunk));
-    }
-    if (use_cls && N >= r0 && N < r0 + 16) {  // fp32 straight from the accumulators of the owning lanes
-      const int lr = N - r0, g = lane >> 2, tq = lane & 3;
-      float* dc = d_cls + ((static_cast<int64_t>(b) * T + t) * 3 + which) * D + h * HD;
-      if ((lr & 7) == g) {
-        const int hh = lr >> 3;
-#pragma unroll
-        for (int nd = 0; nd < 8; ++nd)
-          *reinterpret_cast<float2*>(dc + nd * 8 + tq * 2) = make_float2(tile[nd][2 * hh], tile[nd][2 * hh + 1]);
-      }
-    }
-    __syncwarp();
-  };
-  const int ntile = (S + 15) >> 4;
-#pragma unroll 1
-  for (int tile = warp; tile < ntile; tile += SPB_WARPS) {
-    float dq[8][4];
-    attn_bwd_dq_tile(sQ, sK, sV, sdO, s_lse, s_D, tile * 16, S, -1, scale_log2, scale, dq);
-    flush(tile * 16, 0, dq);
-  }
-#pragma unroll 1
-  for (int tile = warp; tile < ntile; tile += SPB_WARPS) {
-    float dk[8][4], dv[8][4];
-    attn_bwd_dkv_tile(sQ, sK, sV, sdO, s_lse, s_D, tile * 16, S, -1, scale_log2, scale, dk, dv);
-    flush(tile * 16, 1, dk);
-    flush(tile * 16, 2, dv);
-  }
-}
-
-// d_qkv[cls_row0+b, :] (bf16) = sum_t d_cls[b,t,:]   (3*D columns)
-__global__ void cls_grad_reduce_kernel(const float* __restrict__ d_cls, __nv_bfloat16* __restrict__ d_qkv, int64_t ld, int T,
-                                       int cols, int64_t cls_row0) {
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    float s = 0.f;
-    for (int t = 0; t < T; ++t) s += d_cls[(static_cast<int64_t>(b) * T + t) * cols + c];
-    d_qkv[(cls_row0 + b) * ld + c] = __float2bfloat16(s);
-  }
-}
-
 }  // namespace tcow
 
 extern "C" int tcow_attn_temporal_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* d_out,
@@ -494,34 +363,12 @@ extern "C" int tcow_attn_spatial_bwd(const void* qkv, int64_t ld_qkv, const void
     return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: bad argument");
   if (use_cls && (!out_cls || !d_out_cls)) return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: cls buffers missing");
   if (!d_cls) return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: scratch missing");
-  if (N + (use_cls ? 1 : 0) > SPB_ROWS)
-    return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: %d tokens per frame > %d not supported in training", N + (use_cls ? 1 : 0), SPB_ROWS);
+  if (N + (use_cls ? 1 : 0) > 304)
+    return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: %d tokens per frame > 304 not supported in training", N + (use_cls ? 1 : 0));
   if ((ld_qkv % 8) || (ld_out % 8) || (ld_do % 8) || (ld_dqkv % 8)) return set_error(TCOW_ERR_ARG, "attn_spatial_bwd: pitches must be multiples of 8");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // tcgen05/TMEM kernels (attn_spatial_bwd_tc.cu) by default; TCOW_SPATIAL_BWD_IMPL=mma selects the mma.sync kernel below
-  // (the independent implementation the tensor-memory kernels are tested against).
-  static const bool force_mma = [] { const char* e = getenv("TCOW_SPATIAL_BWD_IMPL"); return e && e[0] == 'm'; }();
-  if (!force_mma)
-    return launch_spatial_bwd_tc(qkv, ld_qkv, out, ld_out, out_cls, d_out, ld_do, d_out_cls, lse, d_qkv, ld_dqkv, d_cls,
-                                 d_cls + static_cast<int64_t>(B) * T * 3 * heads * 64, B, N, T, heads, use_cls ? 1 : 0,
-                                 cls_row0, s);
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_spatial_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM);
-    if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured[dev & 63] = true;
-  }
-  attn_spatial_bwd_kernel<<<B * T * heads, SPB_WARPS * 32, SPB_SMEM, s>>>(
-      static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<const __nv_bfloat16*>(out), ld_out, out_cls,
-      static_cast<const __nv_bfloat16*>(d_out), ld_do, d_out_cls, lse, static_cast<__nv_bfloat16*>(d_qkv), ld_dqkv, d_cls, B, N,
-      T, heads, use_cls ? 1 : 0, cls_row0, 0.125f * 1.4426950408889634f, 0.125f);
-  int rc = check_launch("attn_spatial_bwd_kernel");
-  if (rc) return rc;
-  if (use_cls) {
-    cls_grad_reduce_kernel<<<B, 256, 0, s>>>(d_cls, static_cast<__nv_bfloat16*>(d_qkv), ld_dqkv, T, 3 * heads * HD, cls_row0);
-    rc = check_launch("cls_grad_reduce_kernel");
-  }
-  return rc;
+  // tcgen05/TMEM kernels (attn_spatial_bwd_tc.cu): pass Q with the queries on the TMEM lanes, pass KV with the keys
+  return launch_spatial_bwd_tc(qkv, ld_qkv, out, ld_out, out_cls, d_out, ld_do, d_out_cls, lse, d_qkv, ld_dqkv, d_cls,
+                               d_cls + static_cast<int64_t>(B) * T * 3 * heads * 64, B, N, T, heads, use_cls ? 1 : 0,
+                               cls_row0, s);
 }

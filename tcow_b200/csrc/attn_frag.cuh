@@ -101,7 +101,8 @@ __device__ __forceinline__ void temporal_attend_seq(uint32_t sQ, uint32_t sK, ui
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float p = exp2f(s[mt][nt][c] - mx[c >> 1]);
+          float p;   // masked entries are -inf: ex2.approx gives exactly 0
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(s[mt][nt][c] - mx[c >> 1]));
           s[mt][nt][c] = p;
           sum[c >> 1] += p;
         }
@@ -153,108 +154,6 @@ __device__ __forceinline__ void temporal_attend_seq(uint32_t sQ, uint32_t sK, ui
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw_addr(sQ, r0 + lrow, nd) + tq * 4), "r"(v) : "memory");
         }
   }
-  __syncwarp();
-}
-
-
-// Same attention for ONE 16-row m-tile of a sequence (query rows [m0, m0+16), m0 a multiple of 16): the unit of work
-// when several warps share a sequence (qkv_tattn.cu).  Key tiles entirely above the causal diagonal are skipped.
-template <int T_PAD>
-__device__ __forceinline__ void temporal_attend_mtile(uint32_t sQ, uint32_t sK, uint32_t sV, int r0, int m0, int T,
-                                                      int causal_diag, float scale_log2) {
-  constexpr int NT = T_PAD / 8;
-  constexpr int KT = T_PAD / 16;
-  const int lane = lane_id();
-  const int g = lane >> 2, tq = lane & 3;
-  // keys >= klim are invisible to every row of this m-tile
-  int klim = T;
-  if (causal_diag >= 0 && m0 + 16 + causal_diag < klim) klim = m0 + 16 + causal_diag;
-  const int kt_used = (klim + 15) >> 4;  // 16-key steps that contain a visible key
-  uint32_t qa[4][4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) load_a_frag(sQ, r0 + m0, ks, qa[ks]);
-  float s[NT][4];
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) s[nt][c] = 0.f;
-#pragma unroll
-  for (int np = 0; np < NT / 2; ++np) {
-    if (np < kt_used) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b[4];
-        load_bk_frag(sK, r0 + np * 16, ks, b);
-        mma_bf16_16816(s[2 * np], qa[ks], b[0], b[1]);
-        mma_bf16_16816(s[2 * np + 1], qa[ks], b[2], b[3]);
-      }
-    }
-  }
-  float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int i = m0 + g + (c >> 1) * 8;
-      const int j = nt * 8 + tq * 2 + (c & 1);
-      const bool ok = (j < T) && (causal_diag < 0 || j <= i + causal_diag);
-      const float v = ok ? s[nt][c] * scale_log2 : -INFINITY;
-      s[nt][c] = v;
-      mx[c >> 1] = fmaxf(mx[c >> 1], v);
-    }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-  }
-  float sum[2] = {0.f, 0.f};
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float p = exp2f(s[nt][c] - mx[c >> 1]);
-      s[nt][c] = p;
-      sum[c >> 1] += p;
-    }
-  float inv_l[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 1);
-    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 2);
-    inv_l[h] = 1.0f / sum[h];
-  }
-  float o[8][4];
-#pragma unroll
-  for (int nd = 0; nd < 8; ++nd)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) o[nd][c] = 0.f;
-#pragma unroll
-  for (int kt = 0; kt < KT; ++kt) {
-    if (kt < kt_used) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * kt][0], s[2 * kt][1]);
-      pa[1] = pack_bf16(s[2 * kt][2], s[2 * kt][3]);
-      pa[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
-      pa[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t b[4];
-        load_bv_frag(sV, r0 + kt * 16, np * 2, b);
-        mma_bf16_16816(o[2 * np], pa, b[0], b[1]);
-        mma_bf16_16816(o[2 * np + 1], pa, b[2], b[3]);
-      }
-    }
-  }
-  __syncwarp();  // every lane has its Q fragments before the rows are overwritten with the output
-#pragma unroll
-  for (int nd = 0; nd < 8; ++nd)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int lrow = m0 + g + h * 8;
-      const uint32_t v = pack_bf16(o[nd][2 * h] * inv_l[h], o[nd][2 * h + 1] * inv_l[h]);
-      if (lrow < T)
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw_addr(sQ, r0 + lrow, nd) + tq * 4), "r"(v) : "memory");
-    }
   __syncwarp();
 }
 

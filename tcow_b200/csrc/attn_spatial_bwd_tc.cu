@@ -11,8 +11,8 @@
 //      broadcast from shared memory: P^T and dS^T (bf16) written back over the consumed columns
 //      -> dV += P^T dO_i, dK += dS^T Q_i (TS MMAs, dO / Q as MN-major operands), columns [128,192) / [192,256)
 // Nothing is transposed in memory, nothing of size S x S leaves the SM, no atomics (the cls token's per-frame gradients
-// go to d_cls and are summed over the frames by cls_grad_reduce, as in the mma.sync version in attn_bwd.cu, which
-// remains the independent implementation these kernels are tested against).
+// go to d_cls and are summed over the frames by cls_grad_reduce_tc_kernel).  Tested against the fp32 autograd of the same
+// attention (tests/gpu_checks_train.py).
 #include <math.h>
 
 #include "ptx.cuh"

@@ -37,12 +37,8 @@ def _f32(t, device):
 
 
 class SeekerEngine:
-    def __init__(self, tracker, max_chunk=8, merge_temporal_proj=True, fuse_temporal_qkv=False):
+    def __init__(self, tracker, max_chunk=8, merge_temporal_proj=True):
         self.max_chunk = max_chunk
-        # qkv projection + temporal attention as one kernel (qkv_tattn.cu: the qkv tensor never reaches HBM).  Measured
-        # 2.5 % slower end to end than the two-kernel form (CTA-pair GEMM, then tcow_attn_temporal) because its mainloop
-        # is still the single-CTA pipeline — off by default until it gets the cta_group::2 mainloop; TCOW_FUSE_TEMPORAL=1.
-        self.fuse_temporal_qkv = fuse_temporal_qkv or os.environ.get('TCOW_FUSE_TEMPORAL', '0') == '1'
         # temporal_fc o temporal_attn.proj has no nonlinearity in between (vit.py:111 -> :174): at inference
         # the two 768x768 linears are pre-multiplied in fp32 into one.
         self.merge_temporal_proj = merge_temporal_proj
@@ -95,9 +91,6 @@ class SeekerEngine:
             w.n1 = (_f32(blk.norm1.weight, device), _f32(blk.norm1.bias, device))
             w.n2 = (_f32(blk.norm2.weight, device), _f32(blk.norm2.bias, device))
             w.t_qkv = (bf(blk.temporal_attn.qkv.weight), _f32(blk.temporal_attn.qkv.bias, device))
-            # head-major regrouping [q_h | k_h | v_h] for the fused qkv + temporal attention kernel
-            perm = torch.arange(3 * D, device=device).reshape(3, HEADS, D // HEADS).permute(1, 0, 2).reshape(-1)
-            w.t_qkv_perm = (w.t_qkv[0][perm].contiguous(), w.t_qkv[1][perm].contiguous())
             Wp, bp = _f32(blk.temporal_attn.proj.weight, device), _f32(blk.temporal_attn.proj.bias, device)
             Wf, bfc = _f32(blk.temporal_fc.weight, device), _f32(blk.temporal_fc.bias, device)
             if self.merge_temporal_proj:
@@ -144,7 +137,7 @@ class SeekerEngine:
         return pk
 
     def packed(self, mod, device):
-        stamp = (self._stamp(mod), self.merge_temporal_proj)  # fuse_temporal_qkv needs no repack (both forms are packed)
+        stamp = (self._stamp(mod), self.merge_temporal_proj)
         with self._lock:
             hit = self._packed.get(device.index)
             if hit is not None and hit[0] == stamp:
@@ -290,7 +283,7 @@ class SeekerEngine:
             L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained), qpv, sample0,
               frame_scale, nbytes=in_bytes + 2.0 * M * Kp)
         # ---- everything from the embeddings to the head GEMM: engine-owned buffers only -> CUDA-graph replay
-        key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, self.fuse_temporal_qkv, self.fuse_ln,
+        key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, self.fuse_ln,
                bool(mod.norm_embeddings), id(pk), fused_embed)
         core = lambda: self._core(mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag, fused_embed)
         if self.use_cuda_graph and self.profile is None:
@@ -352,13 +345,9 @@ class SeekerEngine:
             residual('gemm_patch', PM, (pk.patch_w, None), M, pk.blocks[0].tn1, M)   # + temporal_norm1 of block 0
         for bi, w in enumerate(pk.blocks):
             # temporal attention + temporal_fc + residual (vit.py:169-176); cls rows untouched.  A = LN_tn1(X[:M]).
-            if self.fuse_temporal_qkv:
-                L('qkv_tattn', ops.qkv_temporal_attn, A[:M], w.t_qkv_perm[0], w.t_qkv_perm[1], O, Bc * N, T, HEADS,
-                  causal_diag, flops=2.0 * M * 3 * D * D + 4.0 * Bc * N * HEADS * T * T * 64, nbytes=4.0 * M * D)
-            else:
-                G('gemm_qkv', A[:M], w.t_qkv[0], w.t_qkv[1], QKV[:M], EPI_BF16)
-                L('attn_temporal', ops.attn_temporal, QKV, O, Bc * N, T, HEADS, causal_diag,
-                  flops=4.0 * Bc * N * HEADS * T * T * 64, nbytes=8.0 * M * D)
+            G('gemm_qkv', A[:M], w.t_qkv[0], w.t_qkv[1], QKV[:M], EPI_BF16)
+            L('attn_temporal', ops.attn_temporal, QKV, O, Bc * N, T, HEADS, causal_diag,
+              flops=4.0 * Bc * N * HEADS * T * T * 64, nbytes=8.0 * M * D)
             # norm1 for the spatial branch; the cls rows enter the spatial attention through norm1 too (vit.py:180-186):
             # they follow the patch rows in X, so the stand-alone LayerNorm covers them in the same launch
             n1_rows = R if (use_cls and not fuse_ln) else M

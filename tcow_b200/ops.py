@@ -70,18 +70,6 @@ def attn_temporal(qkv, out, num_seq, T, heads, causal_diag):
     return out
 
 
-def qkv_temporal_attn(a, w_perm, bias_perm, out, num_seq, T, heads, causal_diag):
-    """out[num_seq*T, heads*64] = temporal attention of (a @ w^T + b); w/bias rows regrouped head-major [q|k|v]."""
-    _chk(a, torch.bfloat16, 'qkv_temporal_attn.a'); _chk(w_perm, torch.bfloat16, 'qkv_temporal_attn.w')
-    _chk(bias_perm, torch.float32, 'qkv_temporal_attn.bias'); _chk(out, torch.bfloat16, 'qkv_temporal_attn.out')
-    K = a.shape[1]
-    if a.shape[0] < num_seq * T or w_perm.shape != (heads * 192, K) or out.shape[1] != heads * 64:
-        raise ValueError('qkv_temporal_attn: shape mismatch')
-    _lib.call('tcow_qkv_temporal_attn', a.data_ptr(), a.stride(0), w_perm.data_ptr(), w_perm.stride(0),
-              bias_perm.data_ptr(), out.data_ptr(), out.stride(0), num_seq, T, heads, K, causal_diag, _stream())
-    return out
-
-
 def attn_spatial(qkv, out, out_cls, B, N, T, heads, use_cls, cls_row0):
     _chk(qkv, torch.bfloat16, 'attn_spatial.qkv'); _chk(out, torch.bfloat16, 'attn_spatial.out')
     if out_cls is not None:

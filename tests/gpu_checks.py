@@ -144,34 +144,6 @@ def check_attn_temporal(num_seq, T, causal_diag, heads=12):
     return max(err, untouched), 0.03, f'attn_temporal seq={num_seq} T={T} diag={causal_diag}'
 
 
-def check_qkv_tattn(num_seq, T, causal_diag, heads=12, K=768):
-    """Fused kernel vs the two-kernel form (GEMM -> tcow_attn_temporal) and vs fp32 math on the same bf16 q,k,v."""
-    d = _dev()
-    g = torch.Generator(device=d).manual_seed(7)
-    D = heads * 64
-    M = num_seq * T
-    a = (torch.randn(M + 2, K, device=d, generator=g) * 0.7).to(torch.bfloat16)
-    w = (torch.randn(3 * D, K, device=d, generator=g) * 0.06).to(torch.bfloat16)
-    bias = torch.randn(3 * D, device=d, generator=g) * 0.2
-    perm = torch.arange(3 * D, device=d).reshape(3, heads, 64).permute(1, 0, 2).reshape(-1)
-    qkv = torch.empty(M, 3 * D, device=d, dtype=torch.bfloat16)
-    ref = torch.zeros(M + 2, D, device=d, dtype=torch.bfloat16)
-    ops.gemm(a[:M], w, bias, qkv, ops.EPI_BF16)
-    ops.attn_temporal(qkv, ref, num_seq, T, heads, causal_diag)
-    out = torch.zeros(M + 2, D, device=d, dtype=torch.bfloat16)
-    ops.qkv_temporal_attn(a[:M], w[perm].contiguous(), bias[perm].contiguous(), out, num_seq, T, heads, causal_diag)
-    torch.cuda.synchronize()
-    err = (out.float() - ref.float()).abs().max().item()
-    # and against fp32 math
-    x = (a[:M].float() @ w.float().t() + bias).to(torch.bfloat16).float().reshape(num_seq, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
-    mask = torch.ones(T, T, dtype=torch.bool, device=d).tril(causal_diag) if causal_diag >= 0 else None
-    ref32 = _mha_ref(x[0], x[1], x[2], mask).permute(0, 2, 1, 3).reshape(M, D)
-    err32 = (out[:M].float() - ref32).abs().max().item()
-    untouched = out[M:].abs().max().item()
-    return max(err, err32, untouched), 0.035, \
-        f'qkv_tattn seq={num_seq} T={T} diag={causal_diag} (vs two-kernel {err:.4f}, vs fp32 {err32:.4f})'
-
-
 def check_attn_spatial(B, N, T, use_cls, heads=12):
     d = _dev()
     g = torch.Generator(device=d).manual_seed(3)
@@ -328,16 +300,6 @@ ALL_CHECKS = [
     ('attn_temporal_T60', lambda: check_attn_temporal(33, 60, 0)),
     ('attn_temporal_T33_d2', lambda: check_attn_temporal(5, 33, 2)),
     ('attn_temporal_T1', lambda: check_attn_temporal(4, 1, 0)),
-    ('qkv_tattn_T30', lambda: check_qkv_tattn(602, 30, 0)),
-    ('qkv_tattn_T30_full', lambda: check_qkv_tattn(9, 30, -1)),
-    ('qkv_tattn_T6_d1', lambda: check_qkv_tattn(53, 6, 1)),
-    ('qkv_tattn_T60', lambda: check_qkv_tattn(7, 60, 0)),
-    ('qkv_tattn_T33_d2', lambda: check_qkv_tattn(5, 33, 2)),
-    ('qkv_tattn_T1', lambda: check_qkv_tattn(200, 1, 0)),
-    ('qkv_tattn_T32', lambda: check_qkv_tattn(17, 32, 0)),
-    ('qkv_tattn_T64', lambda: check_qkv_tattn(5, 64, 3)),
-    ('qkv_tattn_T17', lambda: check_qkv_tattn(29, 17, -1)),
-    ('qkv_tattn_big', lambda: check_qkv_tattn(2400, 30, 0)),
     ('attn_spatial_301', lambda: check_attn_spatial(2, 300, 3, True)),
     ('attn_spatial_300_nocls', lambda: check_attn_spatial(1, 300, 2, False)),
     ('attn_spatial_7', lambda: check_attn_spatial(2, 6, 4, True)),

@@ -26,9 +26,6 @@ for _ in range(reps):
         ops.attn_spatial(qkv, out, ocls, B, N, T, H, True, M)
     elif op == 'temporal':
         ops.attn_temporal(qkv, out, B * N, T, H, 0)
-    elif op == 'fq':
-        a_ = x[:M].to(torch.bfloat16) if 'a_' not in dir() else a_
-        ops.qkv_temporal_attn(a_, wq, bq, out, B * N, T, H, 0)
     elif op == 'ln':
         gm = torch.ones(D, device=d); bt = torch.zeros(D, device=d)
         ops.layernorm(x, gm, bt, out)
@@ -41,8 +38,6 @@ for _ in range(ITERS):
         ops.attn_spatial(qkv, out, ocls, B, N, T, H, True, M)
     elif op == 'temporal':
         ops.attn_temporal(qkv, out, B * N, T, H, 0)
-    elif op == 'fq':
-        ops.qkv_temporal_attn(a_, wq, bq, out, B * N, T, H, 0)
 e1.record()
 torch.cuda.synchronize()
 print(op, os.path.basename(os.environ.get('TCOW_B200_LIB', 'default')), 'avg us', e0.elapsed_time(e1) * 1000 / ITERS)
