@@ -214,23 +214,29 @@ __global__ void __launch_bounds__(128) attn_temporal_bwd_kernel(const __nv_bfloa
   const int D = heads * HD;
   const int g = lane >> 2, tq = lane & 3;
 
-  const __nv_bfloat16* src = qkv + static_cast<int64_t>(seq) * T * ld_qkv + head * HD;
-  for (int idx = lane; idx < T * 8 * 3; idx += 32) {
-    const int which = idx / (T * 8), rem = idx % (T * 8);
-    const int row = rem >> 3, chunk = rem & 7;
-    cp_async_16(sw_addr(sQ + which * TILE, row, chunk), src + static_cast<int64_t>(row) * ld_qkv + which * D + chunk * 8);
+  // loads without index divisions: lane = (row mod 4, 16-byte chunk)
+  const int lrow = lane >> 3, lchunk = lane & 7;
+  const __nv_bfloat16* src = qkv + static_cast<int64_t>(seq) * T * ld_qkv + head * HD + lchunk * 8;
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    const __nv_bfloat16* p = src + which * D + static_cast<int64_t>(lrow) * ld_qkv;
+#pragma unroll 4
+    for (int row = lrow; row < T; row += 4, p += 4 * ld_qkv) cp_async_16(sw_addr(sQ + which * TILE, row, lchunk), p);
   }
-  for (int idx = lane; idx < T * 8; idx += 32) {
-    const int row = idx >> 3, chunk = idx & 7;
-    cp_async_16(sw_addr(sdO, row, chunk), d_out + (static_cast<int64_t>(seq) * T + row) * ld_do + head * HD + chunk * 8);
-    cp_async_16(sw_addr(sO, row, chunk), out + (static_cast<int64_t>(seq) * T + row) * ld_out + head * HD + chunk * 8);
+  {
+    const __nv_bfloat16* pd = d_out + (static_cast<int64_t>(seq) * T + lrow) * ld_do + head * HD + lchunk * 8;
+    const __nv_bfloat16* po = out + (static_cast<int64_t>(seq) * T + lrow) * ld_out + head * HD + lchunk * 8;
+#pragma unroll 4
+    for (int row = lrow; row < T; row += 4, pd += 4 * ld_do, po += 4 * ld_out) {
+      cp_async_16(sw_addr(sdO, row, lchunk), pd);
+      cp_async_16(sw_addr(sO, row, lchunk), po);
+    }
   }
   cp_async_commit();
-  for (int idx = lane; idx < (T_PAD - T) * 8 * 5; idx += 32) {  // zero the padding rows of all five tiles
-    const int which = idx / ((T_PAD - T) * 8), rem = idx % ((T_PAD - T) * 8);
-    const int row = T + (rem >> 3), chunk = rem & 7;
-    asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sw_addr(sQ + which * TILE, row, chunk)), "r"(0) : "memory");
-  }
+#pragma unroll
+  for (int which = 0; which < 5; ++which)   // zero the padding rows of all five tiles
+    for (int row = T + lrow; row < T_PAD; row += 4)
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sw_addr(sQ + which * TILE, row, lchunk)), "r"(0) : "memory");
   cp_async_wait<0>();
   __syncwarp();
 
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(128) attn_temporal_bwd_kernel(const __nv_bfloa
 #pragma unroll
     for (int nt = 0; nt < T_PAD / 8; ++nt)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) sum[c >> 1] += exp2f(s[nt][c] - mx[c >> 1]);
+      for (int c = 0; c < 4; ++c) sum[c >> 1] += ex2f(s[nt][c] - mx[c >> 1]);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 1);
