@@ -38,7 +38,6 @@ extern "C" {
 #define TCOW_EPI_BF16_GELU 1 /* C(bf16)  = gelu_erf(A W^T + bias)             (Mlp.fc1+act: vit.py:55-56) */
 #define TCOW_EPI_F32_STORE 2 /* C(fp32)  = A W^T + bias                       (head: mask_tracker.py:113) */
 #define TCOW_EPI_F32_ADD 3   /* C(fp32) += A W^T + bias   (proj/temporal_fc/fc2 + residual: vit.py:176,215-216) */
-#define TCOW_EPI_F32_ADD_LN 4 /* internal: F32_ADD followed by the LayerNorm tail of tcow_gemm_bf16_add_ln */
 #define TCOW_EPI_BF16_GELU_AUX 5 /* training fc1: aux(bf16) = z = A W^T + bias and C(bf16) = gelu_erf(z) (vit.py:55-56) */
 #define TCOW_EPI_F32_ADD_SCALED 7 /* internal: the stochastic-depth residual epilogue of tcow_gemm_bf16_add_scaled     */
 #define TCOW_EPI_BF16_DGELU 6    /* backward of the above: C(bf16) = (A W^T) * gelu_erf'(aux)                      */
@@ -54,14 +53,6 @@ int tcow_check_device(void);
  * Replaces nn.Linear at vit.py:50-52,73-74,146, mask_tracker.py:83-86 and the Conv2d at vit.py:233. */
 int tcow_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                    int64_t ldc, int M, int N, int K, int epilogue, void* stream);
-
-/* Residual GEMM with the NEXT LayerNorm fused in (vit.py:176/215/216 followed by :172/186/216's norm):
- *   X[M,768] (fp32) += A W^T + bias;   ln_out[r,:] (bf16) = LayerNorm(X[r,:]; gamma, beta, eps) for r < ln_rows
- * Each CTA walks all column tiles of its rows, so the rows it has just updated are complete and still L2-resident
- * when it normalises them: the separate LayerNorm pass over HBM disappears.  gamma == NULL: plain bf16 cast. */
-int tcow_gemm_bf16_add_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* X,
-                          int64_t ldx, int M, int N, int K, const float* gamma, const float* beta, float eps,
-                          void* ln_out, int64_t ld_ln, int ln_rows, void* stream);
 
 /* y[rows,D] (bf16) = LayerNorm(x[rows,D] (fp32); gamma, beta, eps) with fp32 statistics
  * (nn.LayerNorm(eps=1e-6): vit.py:135,142,150,428).  gamma == NULL: plain fp32 -> bf16 cast. */

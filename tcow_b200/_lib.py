@@ -21,8 +21,6 @@ SIGNATURES = {
     'tcow_check_device': [],
     'tcow_gemm_bf16': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                        c_int, c_void_p],
-    'tcow_gemm_bf16_add_ln': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
-                              c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p],
     'tcow_layernorm_bf16': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     'tcow_attn_temporal': [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p],
     'tcow_attn_spatial': [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -27,9 +27,8 @@ template <int BN, int EPI, int CL = 1>
 struct GemmCfg {
   static constexpr bool PAIR = (CL == 3);
   static constexpr int CSIZE = (CL == 1) ? 1 : 2;   // CTAs per cluster
-  static constexpr bool LN_TAIL = (EPI == TCOW_EPI_F32_ADD_LN);
   static constexpr bool SCALED = (EPI == TCOW_EPI_F32_ADD_SCALED);  // stochastic depth: per-row scale of the branch
-  static constexpr bool RED_ADD = (EPI == TCOW_EPI_F32_ADD || LN_TAIL || SCALED);
+  static constexpr bool RED_ADD = (EPI == TCOW_EPI_F32_ADD || SCALED);
   static constexpr bool OUT_F32 = (EPI == TCOW_EPI_F32_STORE || RED_ADD);
   // training epilogues: GELU_AUX also stores the pre-activation (second TMA store through tmAux); DGELU multiplies
   // the accumulator by gelu'(z), z read from the saved pre-activation
@@ -38,10 +37,7 @@ struct GemmCfg {
   static constexpr bool GELU_LIKE = (EPI == TCOW_EPI_BF16_GELU || GELU_AUX || DGELU);
   // The GELU epilogue is issue-bound (exact-erf on 128x256 values per tile): give it 8 warps, 4 otherwise.
   static constexpr int EPI_WARPS = (GELU_LIKE && BN >= 128) ? 8 : 4;
-  // LN-tail mode: 4 more warps do nothing but the LayerNorm read-back, so that its (latency-bound) L2/HBM round trips
-  // overlap the epilogue instead of extending it.
-  static constexpr int LN_WARPS = (EPI == TCOW_EPI_F32_ADD_LN) ? 4 : 0;
-  static constexpr int THREADS = 128 + 32 * EPI_WARPS + 32 * LN_WARPS;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // pair mode: each CTA holds half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -131,10 +127,6 @@ __device__ __forceinline__ uint64_t dgelu_erf2(float x0, float x1) {
   return f2_fma(f2_mul(f2_pack(x0, x1), f2_pack(0.3989422804014327f, 0.3989422804014327f)), e, Phi);
 }
 
-// LayerNorm tail of the residual epilogue (EPI_F32_ADD_LN): once a warp's TMA reduce-adds for ALL column tiles of its
-// 32 rows have completed, the rows of the updated fp32 stream are complete in L2; the warp reads them back (L2 hits,
-// they were just written), normalises with fp32 statistics and writes the bf16 operand of the NEXT GEMM — the
-// separate LayerNorm pass over HBM (vit.py:135,142,150) disappears.  gamma == nullptr: plain bf16 cast.
 // Stochastic-depth form of the residual epilogue (DropPath, vit_utils.py:139-164 applied at vit.py:172,186,216):
 //   X[r,:] += row_scale[r] * acc[r,:] + bias_scale[r] * bias + bias2
 struct RowScale {
@@ -143,69 +135,6 @@ struct RowScale {
   const float* bias2;
 };
 
-struct LnTail {
-  const float* x;        // the fp32 stream the GEMM accumulates into (C)
-  int64_t ldx;
-  const float* gamma;
-  const float* beta;
-  __nv_bfloat16* out;
-  int64_t ld_out;
-  int rows;              // rows [0, rows) get normalised
-  float eps;
-};
-
-template <int NV>  // width = NV * 128
-__device__ __forceinline__ void ln_tail_rows(const LnTail& ln, int row0, int nrows) {
-  const int lane = lane_id();
-  constexpr float inv_d = 1.0f / (NV * 128);
-#pragma unroll 1
-  for (int r = 0; r < nrows; r += 4) {  // four rows in flight per iteration
-    float4 v[4][NV];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int row = row0 + r + u;
-      if (r + u < nrows) {
-        const float4* xr = reinterpret_cast<const float4*>(ln.x + static_cast<int64_t>(row) * ln.ldx);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[u][i] = __ldcg(xr + i * 32 + lane);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (r + u >= nrows) continue;
-      uint2* yr = reinterpret_cast<uint2*>(ln.out + static_cast<int64_t>(row0 + r + u) * ln.ld_out);
-      if (ln.gamma == nullptr) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-          yr[i * 32 + lane] = make_uint2(pack_bf16(v[u][i].x, v[u][i].y), pack_bf16(v[u][i].z, v[u][i].w));
-        continue;
-      }
-      float sm = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) sm += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-      const float mean = sm * inv_d;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float a0 = v[u][i].x - mean, a1 = v[u][i].y - mean, a2 = v[u][i].z - mean, a3 = v[u][i].w - mean;
-        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      const float rstd = rsqrtf(q * inv_d + ln.eps);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(ln.gamma) + i * 32 + lane);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ln.beta) + i * 32 + lane);
-        yr[i * 32 + lane] = make_uint2(pack_bf16((v[u][i].x - mean) * rstd * g.x + b.x, (v[u][i].y - mean) * rstd * g.y + b.y),
-                                       pack_bf16((v[u][i].z - mean) * rstd * g.z + b.z, (v[u][i].w - mean) * rstd * g.w + b.w));
-      }
-    }
-  }
-}
-
 // CL = 1: stand-alone CTAs.  CL = 2: clusters of two CTAs working on vertically adjacent 128-row tiles of the same
 // n-block; each CTA fetches half of the shared weight tile and TMA-multicasts it to both, which cuts the L2->SM
 // operand traffic per CTA from 48 KB to 32 KB per k-block (the mainloop's real limiter at ~14 TB/s of L2 reads).
@@ -213,7 +142,7 @@ template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GemmCfg<BN, EPI, CL>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
-                    const LnTail ln, const __grid_constant__ CUtensorMap tmAux, const __nv_bfloat16* __restrict__ aux,
+                    const __grid_constant__ CUtensorMap tmAux, const __nv_bfloat16* __restrict__ aux,
                     int64_t ldaux, const RowScale rsc) {
   using Cfg = GemmCfg<BN, EPI, CL>;
   constexpr int STAGES = Cfg::STAGES;
@@ -229,10 +158,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
-  // LN-tail hand-off, per epilogue warp w and unit parity p: ln_ready (rows of the unit are final in memory) /
-  // ln_done (the LN warp has consumed them; ring of depth two)
-  auto ln_ready = [&](int w, int p) { return bars + 8u * (2 * STAGES + 6 + w * 2 + p); };
-  auto ln_done = [&](int w, int p) { return bars + 8u * (2 * STAGES + 14 + w * 2 + p); };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5;
@@ -244,20 +169,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
   const int num_munits = (num_m + CS - 1) / CS;
   const int unit0 = blockIdx.x / CS, unit_step = gridDim.x / CS;
-  // k-th tile of this CTA (cluster).  Default: tiles are dealt round-robin, n fastest (neighbouring CTAs share the A
-  // rows in L2).  LN-tail mode: a CTA takes whole row units and walks all their column tiles back to back, so that
-  // every output row is complete (and still L2-resident) when its LayerNorm tail runs.
+  // k-th tile of this CTA (cluster): tiles are dealt round-robin, n fastest (neighbouring CTAs share the A rows in L2).
   auto tile_at = [&](int k, int& m_unit, int& n_blk) -> bool {
-    if constexpr (Cfg::LN_TAIL) {
-      m_unit = unit0 + (k / num_n) * unit_step;
-      n_blk = k % num_n;
-      return m_unit < num_munits;
-    } else {
-      const int lin = unit0 + k * unit_step;
-      m_unit = lin / num_n;
-      n_blk = lin % num_n;
-      return lin < num_munits * num_n;
-    }
+    const int lin = unit0 + k * unit_step;
+    m_unit = lin / num_n;
+    n_blk = lin % num_n;
+    return lin < num_munits * num_n;
   };
 
   if (warp == 0 && lane == 0) {
@@ -275,13 +192,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 32 * Cfg::EPI_WARPS);  // pair: both CTAs' epilogues report to the leader
-    }
-    if (Cfg::LN_TAIL) {
-      for (int w = 0; w < 4; ++w)
-        for (int pp = 0; pp < 2; ++pp) {
-          mbar_init(ln_ready(w, pp), 1);
-          mbar_init(ln_done(w, pp), 1);
-        }
     }
     fence_mbar_init();
   }
@@ -382,7 +292,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t srow = lane * 128;
     const uint32_t sw = lane & 7;
     uint32_t t = 0, cc = 0;
-    int pend_unit = -1;  // LN-tail mode: local index of the row unit whose hand-off to the LN warp is still owed
     for (int k = 0, m_unit, n_blk; tile_at(k, m_unit, n_blk); ++k, ++t) {
       const int m_blk = m_unit * CS + crank;
       const int acc = t & 1;
@@ -506,50 +415,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_commit_group();
         }
       }
-      if constexpr (Cfg::LN_TAIL) {
-        // The LayerNorm tail of a row unit needs its reduce-adds PERFORMED (not merely read out of smem).  Waiting
-        // right after the unit's last tile would stall behind the write queue, so the hand-off to the LN warp happens
-        // one tile later — after the first tile of the next unit, when only that tile's CHUNKS_PER_WARP groups may
-        // still be in flight and the rows are still L2-resident.
-        if (n_blk == 0 && pend_unit >= 0) {
-          if (elect_one()) {
-            tma_wait_group<Cfg::CHUNKS_PER_WARP>();
-            mbar_wait(ln_done(ew, pend_unit & 1), ((pend_unit >> 1) & 1) ^ 1);  // ring slot free (two units back)
-            mbar_arrive(ln_ready(ew, pend_unit & 1));
-          }
-          __syncwarp();
-          pend_unit = -1;
-        }
-        if (n_blk == num_n - 1) pend_unit = k / num_n;  // complete across all column tiles once these stores land
-      }
-    }
-    if constexpr (Cfg::LN_TAIL) {
-      if (pend_unit >= 0) {
-        if (elect_one()) {
-          tma_wait_group<0>();
-          mbar_wait(ln_done(ew, pend_unit & 1), ((pend_unit >> 1) & 1) ^ 1);
-          mbar_arrive(ln_ready(ew, pend_unit & 1));
-        }
-        __syncwarp();
-      }
     }
     __syncwarp();
     if (elect_one()) tma_wait_group<0>();
-  } else if (Cfg::LN_TAIL && warp >= 4 + Cfg::EPI_WARPS) {
-    // -------------------------------------------------- LayerNorm warps: normalise the rows epilogue warp `ew` has
-    // finished (fp32 stream read back, mostly from L2) into the bf16 operand of the next GEMM.
-    const int ew = warp & 3;
-    int u = 0;
-    for (int k = 0, m_unit, n_blk; tile_at(k, m_unit, n_blk); k += num_n, ++u) {
-      const int m_blk = m_unit * CS + crank;
-      mbar_wait(ln_ready(ew, u & 1), (u >> 1) & 1);
-      const int row0 = m_blk * BM + ew * 32;
-      int nrows = ln.rows - row0;
-      ln_tail_rows<BN * 3 / 128>(ln, row0, nrows < 0 ? 0 : (nrows > 32 ? 32 : nrows));
-      __syncwarp();
-      if (elect_one()) mbar_arrive(ln_done(ew, u & 1));
-      __syncwarp();
-    }
   }
 
   tc_fence_before();
@@ -564,7 +432,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------ host side
 template <int BN, int EPI, int CL>
 static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
-                       int64_t ldc, int M, int N, int K, cudaStream_t stream, const LnTail& ln = LnTail{},
+                       int64_t ldc, int M, int N, int K, cudaStream_t stream,
                        const void* aux = nullptr, int64_t ldaux = 0, const RowScale& rsc = RowScale{}) {
   using Cfg = GemmCfg<BN, EPI, CL>;
   constexpr int CS = Cfg::CSIZE;
@@ -585,7 +453,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
     configured[dev & 63] = true;
   }
   const int num_m = (M + BM - 1) / BM;
-  const int units = ((num_m + CS - 1) / CS) * (Cfg::LN_TAIL ? 1 : (N / BN));
+  const int units = ((num_m + CS - 1) / CS) * (N / BN);
   const int slots = sm_count() / CS;
   const int grid = CS * (units < slots ? units : slots);
   cudaLaunchConfig_t cfg{};
@@ -600,7 +468,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, bias, M, N, K, ln, tmAux,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, bias, M, N, K, tmAux,
                                      static_cast<const __nv_bfloat16*>(aux), ldaux, rsc);
   if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "gemm_bf16_tn_kernel: launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_tn_kernel");
@@ -621,16 +489,15 @@ template <int EPI>
 static int dispatch_bn(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                        int64_t ldc, int M, int N, int K, cudaStream_t stream, const void* aux = nullptr,
                        int64_t ldaux = 0, const RowScale& rsc = RowScale{}) {
-  const LnTail none{};
   if (N % 256 == 0) {
     switch (cluster_mode(M, EPI)) {
-      case 3: return launch_gemm<256, EPI, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
-      case 2: return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
-      default: return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
+      case 3: return launch_gemm<256, EPI, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, aux, ldaux, rsc);
+      case 2: return launch_gemm<256, EPI, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, aux, ldaux, rsc);
+      default: return launch_gemm<256, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, aux, ldaux, rsc);
     }
   }
-  if (N % 128 == 0) return launch_gemm<128, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
-  return launch_gemm<64, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, none, aux, ldaux, rsc);
+  if (N % 128 == 0) return launch_gemm<128, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, aux, ldaux, rsc);
+  return launch_gemm<64, EPI, 1>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, aux, ldaux, rsc);
 }
 
 }  // namespace tcow
@@ -687,22 +554,4 @@ extern "C" int tcow_gemm_bf16_add_scaled(const void* A, int64_t lda, const void*
   const RowScale rsc{row_scale, bias_scale, bias2};
   return dispatch_bn<TCOW_EPI_F32_ADD_SCALED>(A, lda, W, ldw, bias, X, ldx, M, N, K, static_cast<cudaStream_t>(stream),
                                               nullptr, 0, rsc);
-}
-
-extern "C" int tcow_gemm_bf16_add_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* X,
-                                     int64_t ldx, int M, int N, int K, const float* gamma, const float* beta, float eps,
-                                     void* ln_out, int64_t ld_ln, int ln_rows, void* stream) {
-  using namespace tcow;
-  if (!A || !W || !X || !ln_out) return set_error(TCOW_ERR_ARG, "gemm_add_ln: null pointer");
-  if (M <= 0 || K <= 0 || K % 64 != 0) return set_error(TCOW_ERR_ARG, "gemm_add_ln: bad M/K");
-  if (N != 768) return set_error(TCOW_ERR_ARG, "gemm_add_ln: the fused LayerNorm tail needs N = 768 (got %d)", N);
-  if ((gamma == nullptr) != (beta == nullptr)) return set_error(TCOW_ERR_ARG, "gemm_add_ln: gamma and beta go together");
-  if (ln_rows < 0 || ln_rows > M) return set_error(TCOW_ERR_ARG, "gemm_add_ln: ln_rows out of range");
-  if ((ldx % 4) || (ld_ln % 4) || (reinterpret_cast<uintptr_t>(ln_out) & 7))
-    return set_error(TCOW_ERR_ARG, "gemm_add_ln: stream / output pitches must be multiples of 4 elements");
-  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return set_error(TCOW_ERR_ARG, "gemm_add_ln: bias must be 16-byte aligned");
-  LnTail ln{X, ldx, gamma, beta, static_cast<__nv_bfloat16*>(ln_out), ld_ln, ln_rows, eps};
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (M > BM * 2) return launch_gemm<256, TCOW_EPI_F32_ADD_LN, 3>(A, lda, W, ldw, bias, X, ldx, M, N, K, s, ln);
-  return launch_gemm<256, TCOW_EPI_F32_ADD_LN, 1>(A, lda, W, ldw, bias, X, ldx, M, N, K, s, ln);
 }

@@ -42,11 +42,9 @@ class SeekerEngine:
         # temporal_fc o temporal_attn.proj has no nonlinearity in between (vit.py:111 -> :174): at inference
         # the two 768x768 linears are pre-multiplied in fp32 into one.
         self.merge_temporal_proj = merge_temporal_proj
-        # LayerNorm fused into the tail of the preceding residual GEMM (tcow_gemm_bf16_add_ln).  Measured at B=8: SLOWER
-        # (338 vs 365 clips/s) — the 221 MB stream does not stay L2-resident, so the tail re-reads HBM with a fraction of
-        # the stand-alone kernel's memory parallelism, and the row-unit tile order it needs costs the K=3072 GEMM 17 %.
-        # Off by default (TCOW_FUSE_LN=1 enables; profiles/r01_notes.md).
-        self.fuse_ln = os.environ.get('TCOW_FUSE_LN', '0') == '1'
+        # LayerNorm stays a stand-alone bandwidth kernel: both fusions were built and measured slower or equal — a read-back
+        # tail inside the residual GEMM (round 1, -7 %) and the deferred form with statistics applied in the next GEMM's
+        # epilogue (round 2, -0.3 %); numbers in profiles/r01_notes.md and profiles/r02_notes.md.
         # Patch embedding as one kernel (gather + implicit GEMM + embeddings, csrc/patch_embed_fused.cu) whenever the shape
         # allows it (patch 16, T <= 32); TCOW_FUSE_PATCH=0 forces the three-kernel form (gather, embed_init, reduce-add GEMM).
         self.fuse_patch_embed = os.environ.get('TCOW_FUSE_PATCH', '1') != '0'
@@ -272,8 +270,7 @@ class SeekerEngine:
         PM = ws['H'][:M * Kp].view(M, Kp)
         L, G = self._launch, self._gemm
         # ---- patch embedding + embeddings (mask_tracker.py:107-108, vit.py:235-241, vision_tf.py:99-138)
-        fused_embed = (self.fuse_patch_embed and P == 16 and T <= ops.PATCH_EMBED_FUSED_MAX_T and D % 256 == 0
-                       and not self.fuse_ln)
+        fused_embed = self.fuse_patch_embed and P == 16 and T <= ops.PATCH_EMBED_FUSED_MAX_T and D % 256 == 0
         in_bytes = (3.0 * frames.element_size() / qpv + query.element_size()) * M * Kp / 4
         if fused_embed:
             L('patch_embed', ops.patch_embed_fused, frames, query, pk.patch_w, pk.patch_b, pk.pos, pk.time, pk.cls, X, P,
@@ -283,8 +280,7 @@ class SeekerEngine:
             L('patch_gather', ops.patch_gather, frames, query, PM, P, bool(mod.tracker_backbone.pretrained), qpv, sample0,
               frame_scale, nbytes=in_bytes + 2.0 * M * Kp)
         # ---- everything from the embeddings to the head GEMM: engine-owned buffers only -> CUDA-graph replay
-        key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, self.fuse_ln,
-               bool(mod.norm_embeddings), id(pk), fused_embed)
+        key = (query.device.index, Bc, N, T, use_cls, causal, causal_diag, bool(mod.norm_embeddings), id(pk), fused_embed)
         core = lambda: self._core(mod, pk, ws, Bc, M, R, N, T, D, Kp, use_cls, causal, causal_diag, fused_embed)
         if self.use_cuda_graph and self.profile is None:
             with self._lock:
@@ -325,18 +321,12 @@ class SeekerEngine:
             L('embed_init', ops.embed_init, X, pk.patch_b, pk.pos, pk.time, pk.cls, Bc, N, T, D, nbytes=4.0 * R * D)
         Rs = R if use_cls else M
         ln_bytes = lambda rows: 6.0 * rows * D
-        fuse_ln = self.fuse_ln
         final_ln = pk.norm if mod.norm_embeddings else (None, None)
 
         def residual(kind, a, wb, rows, ln_params, ln_rows):
-            """X[:rows] += a @ W^T + b, then A[:ln_rows] = LN(X[:ln_rows]) — fused tail or stand-alone kernel."""
-            if fuse_ln:
-                Mr, K = a.shape
-                self._launch(kind, ops.gemm_add_ln, a, wb[0], wb[1], X[:rows], ln_params[0], ln_params[1], A, ln_rows,
-                             flops=2.0 * Mr * D * K, nbytes=2.0 * (Mr * K + D * K) + 8.0 * Mr * D + 2.0 * ln_rows * D)
-            else:
-                G(kind, a, wb[0], wb[1], X[:rows], EPI_F32_ADD)
-                L('ln', ops.layernorm, X[:ln_rows], ln_params[0], ln_params[1], A[:ln_rows], nbytes=ln_bytes(ln_rows))
+            """X[:rows] += a @ W^T + b (TMA reduce-add epilogue), then A[:ln_rows] = LN(X[:ln_rows])."""
+            G(kind, a, wb[0], wb[1], X[:rows], EPI_F32_ADD)
+            L('ln', ops.layernorm, X[:ln_rows], ln_params[0], ln_params[1], A[:ln_rows], nbytes=ln_bytes(ln_rows))
 
         nblk = len(pk.blocks)
         if fused_embed:     # X already holds the embedded tokens: only temporal_norm1 of block 0 remains
@@ -350,15 +340,12 @@ class SeekerEngine:
               flops=4.0 * Bc * N * HEADS * T * T * 64, nbytes=8.0 * M * D)
             # norm1 for the spatial branch; the cls rows enter the spatial attention through norm1 too (vit.py:180-186):
             # they follow the patch rows in X, so the stand-alone LayerNorm covers them in the same launch
-            n1_rows = R if (use_cls and not fuse_ln) else M
             if w.t_out is not None:
-                residual('gemm_proj', O[:M], w.t_out, M, w.n1, n1_rows)
+                residual('gemm_proj', O[:M], w.t_out, M, w.n1, Rs)
             else:
                 tmp = H[:M, :D]                                                    # H is idle here
                 G('gemm_proj', O[:M], w.t_proj[0], w.t_proj[1], tmp, EPI_BF16)
-                residual('gemm_proj', tmp, w.t_fc, M, w.n1, n1_rows)
-            if use_cls and n1_rows == M:
-                L('ln', ops.layernorm, X[M:R], w.n1[0], w.n1[1], A[M:R], nbytes=ln_bytes(Bc))
+                residual('gemm_proj', tmp, w.t_fc, M, w.n1, Rs)
             # spatial attention + residual (vit.py:179-215); cls is key/query 0 of every frame
             G('gemm_qkv', A[:Rs], w.s_qkv[0], w.s_qkv[1], QKV[:Rs], EPI_BF16)
             S = N + (1 if use_cls else 0)

@@ -40,20 +40,6 @@ def gemm(a, w, bias, out, epilogue):
     return out
 
 
-def gemm_add_ln(a, w, bias, x, gamma, beta, ln_out, ln_rows, eps=1e-6):
-    """x[M,768] += a @ w^T + bias; ln_out[:ln_rows] = LayerNorm(x[:ln_rows]) (bf16), fused in one kernel."""
-    _chk(a, torch.bfloat16, 'gemm_add_ln.a'); _chk(w, torch.bfloat16, 'gemm_add_ln.w')
-    _chk(x, torch.float32, 'gemm_add_ln.x'); _chk(ln_out, torch.bfloat16, 'gemm_add_ln.ln_out')
-    M, K = a.shape
-    N = w.shape[0]
-    if w.shape[1] != K or x.shape[0] != M or x.shape[1] != N or ln_out.shape[1] != N or ln_out.shape[0] < ln_rows:
-        raise ValueError('gemm_add_ln: shape mismatch')
-    _lib.call('tcow_gemm_bf16_add_ln', a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _p(bias), x.data_ptr(),
-              x.stride(0), M, N, K, _p(gamma), _p(beta), float(eps), ln_out.data_ptr(), ln_out.stride(0), int(ln_rows),
-              _stream())
-    return x
-
-
 def layernorm(x, gamma, beta, out, eps=1e-6):
     _chk(x, torch.float32, 'layernorm.x'); _chk(out, torch.bfloat16, 'layernorm.out')
     rows, D = x.shape
