@@ -124,8 +124,10 @@ extern "C" int tcow_attn_spatial(const void* qkv, int64_t ld_qkv, void* out, int
   // K/V resident in shared memory whenever one frame's keys fit (S <= 304: ping-pong kernel), else streamed in 128-key
   // blocks (e.g. 480x640 frames, S = 1201).  TCOW_SPATIAL_IMPL=stream forces the streamed kernel for every S (tests).
   static const char impl = [] { const char* e = getenv("TCOW_SPATIAL_IMPL"); return e ? e[0] : '\0'; }();
-  if (S <= 304 && impl != 's')
+  if (S <= 304 && impl == 'p')
     return launch_spatial_pp(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
+  if (S <= 304 && impl != 's')
+    return launch_spatial_r1(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
   return launch_spatial_stream(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
 }
 
