@@ -5,7 +5,7 @@
 // mask in-kernel and never materialise the score matrix.
 //
 // The temporal kernel (30x30 problems, far below a tcgen05 tile, bandwidth-shaped) uses warp-level mma.sync m16n8k16 bf16
-// with ldmatrix from XOR-swizzled shared memory; the spatial attention is tcgen05/TMEM (attn_spatial_pp.cu for frames of
+// with ldmatrix from XOR-swizzled shared memory; the spatial attention is tcgen05/TMEM (attn_spatial_r1.cu for frames of
 // up to 304 tokens, attn_spatial_tc.cu streamed for longer ones) and only dispatched from here.
 #include <math.h>
 #include <stdlib.h>
@@ -121,11 +121,9 @@ extern "C" int tcow_attn_spatial(const void* qkv, int64_t ld_qkv, void* out, int
   if ((ld_qkv % 8) || (ld_out % 8)) return set_error(TCOW_ERR_ARG, "attn_spatial: row pitches must be multiples of 8");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int S = N + (use_cls ? 1 : 0);
-  // K/V resident in shared memory whenever one frame's keys fit (S <= 304: ping-pong kernel), else streamed in 128-key
+  // K/V resident in shared memory whenever one frame's keys fit (S <= 304: attn_spatial_r1.cu), else streamed in 128-key
   // blocks (e.g. 480x640 frames, S = 1201).  TCOW_SPATIAL_IMPL=stream forces the streamed kernel for every S (tests).
   static const char impl = [] { const char* e = getenv("TCOW_SPATIAL_IMPL"); return e ? e[0] : '\0'; }();
-  if (S <= 304 && impl == 'p')
-    return launch_spatial_pp(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
   if (S <= 304 && impl != 's')
     return launch_spatial_r1(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
   return launch_spatial_stream(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0, s);
@@ -140,7 +138,7 @@ extern "C" int tcow_attn_spatial_train(const void* qkv, int64_t ld_qkv, void* ou
   if ((ld_qkv % 8) || (ld_out % 8)) return set_error(TCOW_ERR_ARG, "attn_spatial_train: row pitches must be multiples of 8");
   if (N + (use_cls ? 1 : 0) > 304)
     return set_error(TCOW_ERR_ARG, "attn_spatial_train: %d tokens per frame > 304 not supported in training", N + (use_cls ? 1 : 0));
-  return launch_spatial_pp(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0,
+  return launch_spatial_r1(qkv, ld_qkv, out, ld_out, out_cls, B, N, T, heads, use_cls ? 1 : 0, cls_row0,
                            static_cast<cudaStream_t>(stream), lse);
 }
 

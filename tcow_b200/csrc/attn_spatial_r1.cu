@@ -348,10 +348,13 @@ attn_spatial_r1_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
         const uint32_t ii = n / nq;
         const int j = n % nq, kb = ii & 1;
         for (int b = 0; b < nblk; ++b, ++kc) {
-          // the next scores (of this tile, or the first block of the group's next tile) as soon as S_b has been read
-          if (b + 1 < nblk || n + 2 < NT) {
+          // the next scores (of this tile, or the first block of the group's next tile) as soon as S_b has been read.  With
+          // one tile per item (nq == 1) the group's next tile is two items on, in the SAME K/V buffer, which is only refilled
+          // after this tile's P V: there the next scores are issued behind it (below).
+          const bool next_in_tile = b + 1 < nblk, next_tile = !next_in_tile && n + 2 < NT;
+          if (next_in_tile || (next_tile && nq >= 2)) {
             mbar_wait(s_free(g), kc & 1);
-            if (b + 1 < nblk) issue_s(n, b + 1);
+            if (next_in_tile) issue_s(n, b + 1);
             else issue_s(n + 2, 0);
           }
           mbar_wait(p_full(g), kc & 1);
@@ -368,6 +371,10 @@ attn_spatial_r1_kernel(const __grid_constant__ CUtensorMap tmQfull, const __grid
             }
           }
           __syncwarp();
+          if (next_tile && nq < 2) {
+            mbar_wait(s_free(g), kc & 1);
+            issue_s(n + 2, 0);
+          }
         }
       }
     }

@@ -1,6 +1,6 @@
 // Spatial attention on the 5th-gen tensor cores (tcgen05 + TMEM) for frames whose keys do NOT fit shared memory:
 // K and V streamed in 128-key blocks (flash attention), two CTAs per SM.  Frames with S = N (+1 cls) <= 304 tokens run the
-// resident-K/V ping-pong kernel of attn_spatial_pp.cu; this file serves S > 304 (480x640 frames: S = 1201) and holds the
+// resident-K/V kernel of attn_spatial_r1.cu; this file serves S > 304 (480x640 frames: S = 1201) and holds the
 // 4-D tensor-map helper both share.  Reference: vit.py:78-111 as called at vit.py:186 on the tokens of vit.py:179-185.
 #include <math.h>
 #include <stdlib.h>

@@ -13,11 +13,9 @@ int make_tmap_nd(void* map, bool is_f32, const void* ptr, int rank, const uint64
                  const uint32_t* box);
 int make_tmap_2d(void* map, bool is_f32, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
                  uint32_t box_inner, uint32_t box_rows);
-// tcgen05/TMEM spatial attention with K/V resident in shared memory, one CTA per SM with two query tiles in flight
-// (attn_spatial_pp.cu); valid for N + use_cls <= 304.  lse != nullptr also writes the per-row log-sum-exp (training).
-int launch_spatial_pp(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N, int T,
-                      int heads, int use_cls, int64_t cls_row0, cudaStream_t stream, float* lse = nullptr);
-// Same contract, one softmax thread per query row with the scores of a 128-key block held in registers (attn_spatial_r1.cu).
+// tcgen05/TMEM spatial attention with K/V resident in shared memory, one CTA per SM with two query tiles in flight, one
+// softmax thread per query row with the scores of a 128-key block held in registers (attn_spatial_r1.cu); valid for
+// N + use_cls <= 304.  lse != nullptr also writes the per-row log-sum-exp (training).
 int launch_spatial_r1(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* out_cls, int B, int N, int T,
                       int heads, int use_cls, int64_t cls_row0, cudaStream_t stream, float* lse = nullptr);
 // 4-D TMA view of the patch rows of a token-row matrix: (column, t, n, b) -> ((b*N+n)*T+t)*ld + column; box = 64 columns

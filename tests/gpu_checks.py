@@ -279,6 +279,12 @@ ALL_CHECKS = [
     ('attn_spatial_305_fallback', lambda: check_attn_spatial(1, 304, 1, True)),
     ('attn_spatial_1', lambda: check_attn_spatial(3, 1, 2, False)),
     ('attn_spatial_many_items', lambda: check_attn_spatial(8, 300, 30, True)),
+    # several items per SM with one / two query tiles per item (the K/V double buffer and the tile stream wrap differently)
+    ('attn_spatial_25_many_items', lambda: check_attn_spatial(2, 24, 30, True)),
+    ('attn_spatial_24_many_items_nocls', lambda: check_attn_spatial(8, 24, 30, False)),
+    ('attn_spatial_101_many_items', lambda: check_attn_spatial(4, 100, 10, True)),
+    ('attn_spatial_131_many_items', lambda: check_attn_spatial(3, 130, 20, True)),
+    ('attn_spatial_201_many_items', lambda: check_attn_spatial(4, 200, 10, True)),
     ('patch_gather', lambda: check_patch_gather(2, 3, 32, 48, False)),
     ('patch_gather_norm', lambda: check_patch_gather(1, 2, 240, 320, True)),
     ('embed_init', lambda: check_embed_init(2, 6, 4)),

@@ -11,7 +11,7 @@ python bench.py --workload hires --steps 10 > gpurun_out/${T}_hires.json 2> gpur
 TCOW_CUDA_GRAPH=0 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1500 --csv \
   --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-train \
   > gpurun_out/${T}_ncu_bench.log 2>&1
-TCOW_CUDA_GRAPH=0 ncu --set full --clock-control none --import-source on -k regex:'attn_spatial_pp|patch_embed_fused|gemm_bf16_tn|attn_temporal|layernorm' \
+TCOW_CUDA_GRAPH=0 ncu --set full --clock-control none --import-source on -k regex:'attn_spatial_r1|patch_embed_fused|gemm_bf16_tn|attn_temporal|layernorm' \
   -s 160 -c 14 -o gpurun_out/${T}_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-train \
   > gpurun_out/${T}_ncu_full.log 2>&1
 ls -la gpurun_out/${T}_*
