@@ -6,7 +6,7 @@
 //
 // The temporal kernel (30x30 problems, far below a tcgen05 tile, bandwidth-shaped) uses warp-level mma.sync m16n8k16 bf16
 // with ldmatrix from XOR-swizzled shared memory; the spatial attention is tcgen05/TMEM (attn_spatial_r1.cu for frames of
-// up to 304 tokens, attn_spatial_tc.cu streamed for longer ones) and only dispatched from here.
+// up to 304 tokens, attn_spatial_rs.cu streamed for longer ones) and only dispatched from here.
 #include <math.h>
 #include <stdlib.h>
 

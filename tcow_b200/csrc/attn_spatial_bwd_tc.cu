@@ -1,5 +1,5 @@
 // Backward of the spatial attention on the 5th-gen tensor cores (tcgen05 + TMEM); two persistent kernels shaped like the
-// forward kernel of attn_spatial_tc.cu, two CTAs per SM each.  With P = softmax(Q K^T/8), dP = dO V^T,
+// round-1 forward kernel (one CTA = one chain of MMA -> softmax -> MMA), two CTAs per SM each.  With P = softmax(Q K^T/8), dP = dO V^T,
 // dS = P o (dP - D)/8, D_i = dO_i . O_i  (autograd of vit.py:88-109 as called at vit.py:186):
 //
 //  pass Q  (queries on the TMEM lanes; work item (b,t,head), K and V resident in shared memory, 128-query tiles):

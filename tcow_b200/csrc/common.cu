@@ -81,6 +81,17 @@ int make_tmap_2d(void* map, bool is_f32, const void* ptr, uint64_t inner, uint64
   return make_tmap_nd(map, is_f32, ptr, 2, dims, strides, box);
 }
 
+// 4-D view of the patch rows of a token-row matrix: (column, t, n, b) -> ((b*N+n)*T+t)*ld + column; box = 64 columns x
+// box_n tokens of one frame (rows T apart), SWIZZLE_128B — what the spatial-attention kernels load and store through.
+int make_patch_tmap(void* m, const void* qkv, int64_t ld, int cols, int B, int N, int T, int box_n) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(T), static_cast<uint64_t>(N),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(T) * ld * 2,
+                               static_cast<uint64_t>(N) * T * ld * 2};
+  const uint32_t box[4] = {64, 1, static_cast<uint32_t>(box_n), 1};
+  return make_tmap_nd(m, false, qkv, 4, dims, strides, box);
+}
+
 }  // namespace tcow
 
 extern "C" int tcow_abi_version(void) { return 1; }
