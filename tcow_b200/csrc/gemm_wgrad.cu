@@ -22,9 +22,8 @@ namespace {
 constexpr int WG_BM = 128;
 constexpr int WG_BK = 64;  // token rows per pipeline stage
 
-template <int BN, int CL = 1>
+template <int BN>
 struct WgCfg {
-  static constexpr int CSIZE = CL;  // CTAs per cluster: 2 = adjacent n1 tiles share the B tile by TMA multicast
   static constexpr int THREADS = 256;
   static constexpr int A_BYTES = WG_BM * WG_BK * 2;
   static constexpr int B_BYTES = BN * WG_BK * 2;
@@ -47,13 +46,12 @@ __host__ __device__ constexpr uint32_t wg_idesc(int M, int N) {
 }
 }  // namespace
 
-template <int BN, int CL>
-__global__ void __launch_bounds__(WgCfg<BN, CL>::THREADS, 1)
+template <int BN>
+__global__ void __launch_bounds__(WgCfg<BN>::THREADS, 1)
 gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, int R, int N1, int N2, int splits, int kb_per_split,
                        float* __restrict__ db, int* __restrict__ sched) {
-  using Cfg = WgCfg<BN, CL>;
-  constexpr int CS = CL;
+  using Cfg = WgCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_wg[];
   const uint32_t raw = smem_u32(smem_wg);
@@ -77,17 +75,16 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
   const int num_m = (N1 + WG_BM - 1) / WG_BM;
   const int num_n = N2 / BN;
-  const int tiles = (num_m / CS) * num_n;   // CS = 2: a unit is two vertically adjacent n1 tiles (num_m is even)
+  const int tiles = num_m * num_n;
   const int num_kb = (R + WG_BK - 1) / WG_BK;
   const int units = tiles * splits;
-  const int unit0 = blockIdx.x / CS, unit_step = gridDim.x / CS;
+  const int unit0 = blockIdx.x, unit_step = gridDim.x;
   // unit -> (tile, split): splits outermost, so the CTAs running at the same time stream the same token rows
   auto unit_at = [&](int u, int& m_blk, int& n_blk, int& kb0, int& kb1) {
     const int sp = u / tiles, tile = u % tiles;
-    m_blk = (tile / num_n) * CS + crank;
+    m_blk = tile / num_n;
     n_blk = tile % num_n;
     kb0 = sp * kb_per_split;
     kb1 = kb0 + kb_per_split < num_kb ? kb0 + kb_per_split : num_kb;
@@ -101,9 +98,8 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      // multicast mode: both CTAs must have drained the stage before either refills it; bias-gradient mode: so must the
-      // two column-sum warps
-      mbar_init(empty_bar(s), CS + (db ? 2 : 0));
+      // bias-gradient mode: the two column-sum warps must have drained the stage too
+      mbar_init(empty_bar(s), 1 + (db ? 2 : 0));
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -121,7 +117,6 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast can land on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // k-th unit of this CTA as published by the producer warp (-1: no more work)
@@ -159,12 +154,7 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
           // box = (64 columns, 64 token rows, column blocks); rows / blocks past the tensor are zero-filled
           tma_load_3d(sa, &tmA, 0, kb * WG_BK, m_blk * (WG_BM / 64), full_bar(s));
-          if (CS == 1) {
-            tma_load_3d(sa + Cfg::A_BYTES, &tmB, 0, kb * WG_BK, n_blk * (BN / 64), full_bar(s));
-          } else {  // my half of the column blocks of B, delivered to both CTAs (the peer sends the other half)
-            tma_load_3d_mcast(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, 0, kb * WG_BK,
-                              n_blk * (BN / 64) + crank * (BN / 128), full_bar(s), static_cast<uint16_t>(3));
-          }
+          tma_load_3d(sa + Cfg::A_BYTES, &tmB, 0, kb * WG_BK, n_blk * (BN / 64), full_bar(s));
         }
         __syncwarp();
       }
@@ -193,8 +183,7 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
           for (int k = 0; k < WG_BK / 16; ++k)  // 16 token rows = 2048 bytes per MMA: +128 in addr>>4 units
             umma_bf16(d_tmem, adesc + 128u * k, bdesc + 128u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          if (CS == 1) umma_commit(empty_bar(s));
-          else umma_commit_mcast(empty_bar(s), static_cast<uint16_t>(3));
+          umma_commit(empty_bar(s));
           if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
@@ -284,7 +273,6 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();  // no CTA exits while its peer may still multicast into it or signal its barriers
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   if (sched && threadIdx.x == 0) {   // the last CTA to leave puts the ticket counters back to zero for the next launch
     __threadfence();
@@ -305,17 +293,16 @@ static int make_mn_tmap(CUtensorMap* m, const void* p, int64_t ld, int R, int C,
   return make_tmap_nd(m, false, p, 3, dims, strides, box);
 }
 
-template <int BN, int CL>
+template <int BN>
 static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, int R, int N1,
                         int N2, float* db, int* sched, cudaStream_t stream) {
-  using Cfg = WgCfg<BN, CL>;
-  constexpr int CS = CL;
+  using Cfg = WgCfg<BN>;
   alignas(64) CUtensorMap tmA, tmB, tmC;
   int rc;
   if ((rc = make_mn_tmap(&tmA, A, lda, R, N1, WG_BM / 64))) return rc;
-  if ((rc = make_mn_tmap(&tmB, B, ldb, R, N2, BN / 64 / CS))) return rc;
+  if ((rc = make_mn_tmap(&tmB, B, ldb, R, N2, BN / 64))) return rc;
   if ((rc = make_tmap_2d(&tmC, true, dW, N2, N1, ldw, 32, 32))) return rc;
-  auto kern = gemm_bf16_wgrad_kernel<BN, CL>;
+  auto kern = gemm_bf16_wgrad_kernel<BN>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -325,9 +312,9 @@ static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, 
     configured[dev & 63] = true;
   }
   // Row splits: fill the SMs (tiles x splits close to a multiple of the SM count) with at least 8 k-blocks each.
-  const int tiles = ((N1 + WG_BM - 1) / WG_BM) / CS * (N2 / BN);   // cluster units
+  const int tiles = ((N1 + WG_BM - 1) / WG_BM) * (N2 / BN);
   const int num_kb = (R + WG_BK - 1) / WG_BK;
-  const int sms = sm_count() / CS;
+  const int sms = sm_count();
   int best = 1;
   double best_eff = 0.0;
   for (int s = 1; s <= 64 && (s == 1 || s * 8 <= num_kb); ++s) {
@@ -346,20 +333,9 @@ static int launch_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, 
   const int per = (num_kb + best - 1) / best;
   const int splits = (num_kb + per - 1) / per;  // no empty split
   const int units = tiles * splits;
-  const int grid = CS * (units < sms ? units : sms);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(Cfg::THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, R, N1, N2, splits, per, db, sched);
+  const int grid = units < sms ? units : sms;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, tmC, R, N1, N2, splits, per, db, sched);
+  const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return set_error(TCOW_ERR_CUDA, "gemm_bf16_wgrad_kernel: launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_wgrad_kernel");
 }
@@ -375,16 +351,10 @@ extern "C" int tcow_gemm_bf16_wgrad_sched(const void* A, int64_t lda, const void
     return set_error(TCOW_ERR_ARG, "wgrad: N1 (%d) and N2 (%d) must be multiples of 64", N1, N2);
   if ((lda % 8) || (ldb % 8) || (ldw % 4)) return set_error(TCOW_ERR_ARG, "wgrad: row pitches must be 16-byte multiples");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // Clusters of two CTAs (adjacent n1 tiles, B tile TMA-multicast) measured SLOWER than stand-alone CTAs for every
-  // weight-gradient shape of the model (qkv 1142 vs 1206, fc2 1129 vs 1199 TFLOP/s: the long row loop keeps the B slab in
-  // L2 anyway, and the cluster couples the two CTAs' stage recycling): off unless TCOW_WGRAD_CLUSTER=2 (never with db).
-  static const bool want_cluster = [] { const char* e = getenv("TCOW_WGRAD_CLUSTER"); return e && e[0] == '2'; }();
-  const bool pairs = ((N1 + WG_BM - 1) / WG_BM) % 2 == 0 && want_cluster && db == nullptr && sched == nullptr;
-  if (N2 % 256 == 0) {
-    if (pairs) return launch_wgrad<256, 2>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, sched, s);
-    return launch_wgrad<256, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, sched, s);
-  }
-  return launch_wgrad<64, 1>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, sched, s);
+  // (Clusters of two CTAs sharing the B tile by TMA multicast measured slower for every weight-gradient shape of the model
+  // — qkv 1142 vs 1206, fc2 1129 vs 1199 TFLOP/s — and are gone: the long row loop keeps the B slab in L2 anyway.)
+  if (N2 % 256 == 0) return launch_wgrad<256>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, sched, s);
+  return launch_wgrad<64>(A, lda, B, ldb, dW, ldw, R, N1, N2, db, sched, s);
 }
 
 extern "C" int tcow_gemm_bf16_wgrad_bias(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
