@@ -113,12 +113,13 @@ def run_sweep(net, items: Sequence[SweepItem], get_video, get_query, get_target,
     results = {}
     groups = group_by_clip(items)
     pending = []
-    vcache, tcache = {}, {}          # the current video (and its targets) live on the device; clips are gathered there
+    vcache, tcache, qcache = {}, {}, {}   # the current video (its targets, its query masks) live on the device; clips are gathered there
 
     def video_on_device(v):
         if v not in vcache:
             vcache.clear()
             tcache.clear()
+            qcache.clear()
             vid = get_video(v).to(device, non_blocking=True)
             # decoded frames arrive as uint8 (data/data_plugin.py:174 divides by 255 on the host): expand on the device
             vcache[v] = vid.float().div_(255.0) if vid.dtype == torch.uint8 else vid.float()
@@ -129,6 +130,13 @@ def run_sweep(net, items: Sequence[SweepItem], get_video, get_query, get_target,
             t = get_target(v, q)
             tcache[(v, q)] = None if t is None else t.to(device, non_blocking=True).float()
         return tcache[(v, q)]
+
+    def query_on_device(v, q):
+        # once per (video, query), not once per clip: a copy from pageable host memory waits for the stream to drain, and one
+        # per sample would serialise the host's preparation of a pass with the device's execution of the previous one
+        if (v, q) not in qcache:
+            qcache[(v, q)] = get_query(v, q).to(device, non_blocking=True)
+        return qcache[(v, q)]
 
     with torch.no_grad():
         for g0 in range(0, len(groups), clips_per_pass):
@@ -144,7 +152,7 @@ def run_sweep(net, items: Sequence[SweepItem], get_video, get_query, get_target,
                 for j in range(nq):
                     it = its[min(j, len(its) - 1)]            # pad ragged groups by repeating the last query
                     q = torch.zeros(1, num_frames, *vid.shape[-2:], device=device)
-                    q[0, it.query_time] = get_query(v, it.query).to(device, non_blocking=True)
+                    q[0, it.query_time] = query_on_device(v, it.query)
                     qs.append(q)
                     t = target_on_device(v, it.query)
                     # a (clip, query) without ground truth gets an all-negative target: every frame is then ignored
